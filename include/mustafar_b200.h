@@ -1,0 +1,170 @@
+/*
+ * mustafar_b200.h — C ABI of libmustafar_b200.so (sm_100a).
+ *
+ * This is the drop-in boundary for the sparse-KV decode path of dhjoo98/mustafar.  Every entry
+ * point takes plain device pointers, sizes and a CUDA stream handle; there are no torch types in
+ * any signature.  All functions are asynchronous on `stream`, never synchronise the host, and
+ * return 0 on success or a negative MFB200_E* code (the message is available from
+ * mfb200_last_error()).  CUDA launch errors are reported, unlike the reference wrapper which drops
+ * them (kernel/kernel_wrapper/mustafar_wrapper.cu:113, :242).
+ *
+ * Reference interfaces each entry point replaces (paths relative to /root/reference):
+ *
+ *   mfb200_prune_rows            models/llama_mustafar_kernel.py:77-113, :117-153  (dh_prune_key/value)
+ *   mfb200_compress_count        kernel/compression.py:9-54, :57-115   (calculate_bitmap_{key,value}_batched)
+ *   mfb200_compress_scan         kernel/compression.py:294-304, :387-397 (torch.cumsum / cat glue)
+ *   mfb200_compress_pack         kernel/compression.py:118-174, :178-247 (compress_{key,value}_batched)
+ *   mfb200_key_formulation       kernel/build/SpMM_API.cuh:46-64  Key_SplitK_API   (csrc/SpMM_API.cu:86-139)
+ *   mfb200_value_formulation     kernel/build/SpMM_API.cuh:92-110 Value_SplitK_API (csrc/SpMM_API.cu:193-254)
+ *   mfb200_decode_plan / mfb200_sparse_decode_attention
+ *                                the fused replacement of models/llama_mustafar_kernel.py:268-320
+ *                                (pad q → Key SpMV → window matmul → softmax → pad P → Value SpMV →
+ *                                window matmul → add); new, not in the reference.
+ *   mfb200_window_append         models/llama_mustafar_kernel.py:270, :309 (torch.cat of the new k/v row)
+ *
+ * Compressed-KV format (normative, SURVEY.md App. A / kernel/compression.py): tile = 64 fp16
+ * elements; bitmap bit (63-e) set iff element e != 0; nonzeros packed in ascending e, zero padded
+ * to a multiple of 8 halves; idx[t] = exclusive prefix of padded sizes in units of 2 halves.
+ * K tile t = token_block*128 + channel (64 consecutive tokens of one channel);
+ * V tile t = token_block*128 + channel_half*64 + token_in_block (64 consecutive channels).
+ */
+#ifndef MUSTAFAR_B200_H
+#define MUSTAFAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFB200_ABI_VERSION 1
+
+#define MFB200_OK 0
+#define MFB200_EINVAL (-1)  /* bad argument (shape, alignment, null pointer) */
+#define MFB200_ECUDA (-2)   /* CUDA runtime / launch error */
+
+#define MFB200_LAYOUT_KEY 0
+#define MFB200_LAYOUT_VALUE 1
+
+#define MFB200_HEAD_DIM 128
+
+typedef void* mfb200_stream_t; /* cudaStream_t */
+
+int mfb200_abi_version(void);
+/* Thread-local, NUL-terminated description of the last error returned on this thread. */
+const char* mfb200_last_error(void);
+
+/* ---- a1: per-token magnitude threshold pruning -------------------------------------------------
+ * y[r, :] = x[r, :] * (|x[r, :]| >= kth_smallest(|x[r, :]|, k)),  rows of 128 fp16.
+ * k = max(1, int(sparsity*128)) is computed by the caller.  x == y (in place) is allowed. */
+int mfb200_prune_rows(const void* x, void* y, int64_t rows, int k, mfb200_stream_t stream);
+
+/* ---- a2/a3: bitmaps + padded per-tile counts ----------------------------------------------------
+ * x: fp16 [heads, tokens, 128] contiguous, tokens % 64 == 0.  If prune_k > 0 the threshold prune of
+ * mfb200_prune_rows is applied on the fly (x itself is not modified).
+ * bitmaps: int64 [heads, tokens*2]; counts: int32 [heads, tokens*2] in units of 2 halves. */
+int mfb200_compress_count(const void* x, int64_t heads, int64_t tokens, int layout, int prune_k,
+                          int64_t* bitmaps, int32_t* counts, mfb200_stream_t stream);
+
+/* ---- a4: exclusive scan ---------------------------------------------------------------------------
+ * accum: int32 [heads, accum_stride], accum[h, tile_offset + t] for t in [0, tiles]; the running
+ * value starts at accum[h, tile_offset] when tile_offset > 0 (append to an existing head) and at 0
+ * otherwise.  head_total (may be NULL): int32 [heads] = accum[h, tile_offset + tiles]. */
+int mfb200_compress_scan(const int32_t* counts, int64_t heads, int64_t tiles, int32_t* accum,
+                         int64_t accum_stride, int64_t tile_offset, int32_t* head_total,
+                         mfb200_stream_t stream);
+
+/* ---- a5/a6: pack nonzeros ---------------------------------------------------------------------------
+ * Writes, for every tile, its nonzeros followed by zero padding at
+ *   packed + head_base[h] + 2*accum[h, tile_offset + t]      (all in halves).
+ * bitmaps/accum as produced above (bitmaps: [heads, tokens*2] of THIS chunk; accum may be the
+ * long-lived per-head array of a cache, addressed through accum_stride/tile_offset).
+ * head_base: int64 [heads], halves, multiple of 8.
+ * head_capacity (halves, 0 = unchecked): a tile that would end beyond head_base[h]+head_capacity is
+ * not written and *overflow (int32, device, may be NULL) is set to 1 — lets a preallocated slab be
+ * smaller than the worst case without risking its neighbours. */
+int mfb200_compress_pack(const void* x, int64_t heads, int64_t tokens, int layout,
+                         const int64_t* bitmaps, const int32_t* accum, int64_t accum_stride,
+                         int64_t tile_offset, const int64_t* head_base, void* packed,
+                         int64_t head_capacity, int32_t* overflow, mfb200_stream_t stream);
+
+/* ---- a8-a13: the two batched SpMV operators, reference argument order ----------------------------------
+ * C[bq, n, m] (fp16 [Batch_Size, 8, M_Global]).  N_Global must be 8, K_Global 128 (key) /
+ * M_Global 128 (value), Split_K is ignored (the reference hard-wires 1).  `A` is unused (NULL in the
+ * reference).  workspace: value op only, >= mfb200_value_workspace_bytes(...) bytes, zero-initialised
+ * once by the caller (the kernel leaves it zeroed). */
+int mfb200_key_formulation(mfb200_stream_t stream, const void* A, const uint64_t* bmp, const void* NZ,
+                           const uint32_t* idx, const uint32_t* NZ_offset, const void* B, void* C,
+                           int M_Global, int N_Global, int K_Global, void* Reduction_Workspace,
+                           int Split_K, int Batch_Size, int num_key_value_groups);
+int mfb200_value_formulation(mfb200_stream_t stream, const void* A, const uint64_t* bmp, const void* NZ,
+                             const uint32_t* idx, const uint32_t* NZ_offset, const void* B, void* C,
+                             int M_Global, int N_Global, int K_Global, void* workspace,
+                             int Split_K, int Batch_Size, int num_key_value_groups);
+size_t mfb200_value_workspace_bytes(int K_Global, int Batch_Size);
+
+/* ---- fused sparse decode attention ------------------------------------------------------------------ */
+typedef struct mfb200_decode_params {
+    /* geometry */
+    int32_t batch;        /* B  */
+    int32_t kv_heads;     /* Hkv */
+    int32_t groups;       /* G = Hq / Hkv, 1..8 */
+    int32_t comp_len;     /* L: tokens in the compressed cache, multiple of 64 (0 allowed) */
+    int32_t win_len;      /* Lw: tokens in the dense window, >= 0; L + Lw >= 1 */
+    int32_t flags;        /* MFB200_F_* */
+    float score_div;      /* sqrt(head_dim): scores are divided by it (llama_mustafar_kernel.py:284) */
+    int32_t n_split;      /* from mfb200_decode_plan */
+    int32_t slot_kb;      /* staging capacity for one 64-token block's nonzeros, KB (1..16); 0 = 16
+                             (worst case, every element kept).  Larger blocks still work: they take a
+                             slower path that reads their nonzeros straight from global memory. */
+    int32_t reserved;
+    /* query / output: fp16 [B, Hq, 128] contiguous */
+    const void* q;
+    void* out;
+    /* compressed K and V.  Per (b, hkv) unit u = b*Hkv + h:
+     *   bitmaps  at  bmp + u*bmp_stride            (uint64, tile order of the layout)
+     *   idx      at  idx + u*idx_stride            (uint32, units of 2 halves, relative to the unit)
+     *   nonzeros at  (uint4*)nz + nz_off[u]        (nz_off in 16-byte units) */
+    const uint64_t* k_bmp;
+    const uint32_t* k_idx;
+    const void* k_nz;
+    const int64_t* k_nz_off;
+    const uint64_t* v_bmp;
+    const uint32_t* v_idx;
+    const void* v_nz;
+    const int64_t* v_nz_off;
+    int64_t bmp_stride; /* in tiles */
+    int64_t idx_stride; /* in entries */
+    /* dense window: fp16, row t of unit u at  win + u*win_stride + t*128 */
+    const void* k_win;
+    const void* v_win;
+    int64_t win_stride; /* halves */
+    /* optional additive mask, fp16 [B, mask_stride], entry t (0 <= t < L+Lw); NULL = none */
+    const void* mask;
+    int64_t mask_stride;
+    /* scratch: >= mfb200_decode_plan() bytes; the counter part must be zero before the first launch
+     * (kernels leave it zeroed). */
+    void* workspace;
+} mfb200_decode_params;
+
+/* Round q·k to fp16 and divide by score_div in fp16 like the reference glue does
+ * (SpMM_Kernel.cuh:418, llama_mustafar_kernel.py:284). Off = keep fp32 scores. */
+#define MFB200_F_REF_SCORE_ROUNDING 1
+
+/* Chooses the number of sequence splits for a launch and reports the workspace size.
+ * sm_count <= 0 → query the current device. Returns n_split (>= 1) or a negative error.
+ * Workspace layout: [counters: units*4 bytes, rounded to 256][partials fp32]. */
+int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count,
+                       size_t* workspace_bytes, size_t* counter_bytes);
+int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb200_stream_t stream);
+
+/* ---- window append (new token's k and v rows) ----------------------------------------------------
+ * win[u, pos, :] = row[u, :] for K and V; row: fp16 [units, 128]. */
+int mfb200_window_append(void* k_win, void* v_win, int64_t win_stride, const void* k_row,
+                         const void* v_row, int64_t units, int64_t pos, mfb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUSTAFAR_B200_H */

@@ -1,0 +1,282 @@
+"""Fused sparse-KV decode attention and the slab KV cache that feeds it.
+
+`MustafarKVCache` holds what the reference keeps in its python tuple cache
+(models/llama_mustafar_kernel.py:445: k_compressed=[bitmaps, accum_counts, [NZ per head], nz_offset],
+k_local_window, v_compressed, v_local_window, compressed_length, kv_seq_len) as PREALLOCATED device
+slabs with the same per-head format, so that
+  * the decode step is one CUDA launch (csrc/decode_attn.cu) instead of the ~15 launches and two
+    whole-cache `torch.cat` copies of llama_mustafar_kernel.py:268-320,
+  * the every-256-token compression (llama_mustafar_kernel.py:324-398) appends in place with no host
+    sync, no `torch.cat` of bitmaps and no `torch.cuda.empty_cache()`.
+The slabs can be handed to the reference-compatible ops too (`as_reference_tuple`).
+
+Schedule (same as the reference): compressed_length = ((T - residual_length)//256)*256 at prefill
+(`:416`); during decode the new token is appended to the dense window BEFORE attention (`:270`,
+`:309`) and when window == residual_length + 256 its first 256 rows are pruned, compressed and
+dropped (`:324`, `:392-398`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .compression import compress_into, pack_into
+from .pruning import HEAD_DIM, prune_rank
+
+COMPRESS_CHUNK = 256  # llama_mustafar_kernel.py:324
+
+
+def compressed_length(kv_seq_len: int, residual_length: int) -> int:
+    """llama_mustafar_kernel.py:416, without its negative result for prompts shorter than the residual."""
+    return max(0, ((kv_seq_len - residual_length) // COMPRESS_CHUNK) * COMPRESS_CHUNK)
+
+
+class _Stream:
+    """bitmaps / accum_counts / packed nonzeros of K or of V for all (sequence, kv-head) units."""
+
+    def __init__(self, units: int, cap_tokens: int, halves_per_token: int, device):
+        self.cap_tiles = cap_tokens * 2
+        self.head_capacity = cap_tokens * halves_per_token  # halves, multiple of 8 (cap_tokens % 64 == 0)
+        self.bmp = torch.zeros((units, self.cap_tiles), dtype=torch.int64, device=device)
+        self.idx = torch.zeros((units, self.cap_tiles + 1), dtype=torch.int32, device=device)
+        self.nz = torch.empty((units * self.head_capacity,), dtype=torch.float16, device=device)
+        self.head_base = torch.arange(units, dtype=torch.int64, device=device) * self.head_capacity  # halves
+        self.nz_off = self.head_base // 8  # uint4 units, int64
+        self.counts_tmp = None
+
+
+class MustafarKVCache:
+    """Preallocated bitmap+packed-nonzero KV cache of one layer with a dense fp16 residual window."""
+
+    def __init__(self, batch: int, kv_heads: int, groups: int, max_tokens: int, k_sparsity: float, v_sparsity: float,
+                 residual_length: int = 32, device="cuda", nz_halves_per_token: Optional[int] = None,
+                 ref_score_rounding: bool = True):
+        self.batch, self.kv_heads, self.groups = batch, kv_heads, groups
+        self.units = batch * kv_heads
+        self.k_sparsity, self.v_sparsity = k_sparsity, v_sparsity
+        self.residual_length = residual_length
+        self.device = torch.device(device)
+        self.ref_score_rounding = ref_score_rounding
+        cap = ((max_tokens + COMPRESS_CHUNK - 1) // COMPRESS_CHUNK) * COMPRESS_CHUNK
+        self.cap_tokens = cap
+        self.win_cap = residual_length + COMPRESS_CHUNK + 1 if residual_length + COMPRESS_CHUNK < max_tokens else max_tokens + 1
+        self.win_cap = max(self.win_cap, residual_length + COMPRESS_CHUNK + 1)
+        self.win_cap = (self.win_cap + 7) // 8 * 8
+
+        def per_token(s):
+            if nz_halves_per_token is not None:
+                return nz_halves_per_token
+            return HEAD_DIM  # worst case: every element of a token survives (ties) -> never overflows
+
+        with torch.cuda.device(self.device):
+            self.k = _Stream(self.units, cap, per_token(k_sparsity), self.device)
+            self.v = _Stream(self.units, cap, per_token(v_sparsity), self.device)
+            self.k_win = torch.zeros((self.units, self.win_cap, HEAD_DIM), dtype=torch.float16, device=self.device)
+            self.v_win = torch.zeros_like(self.k_win)
+            self.overflow = torch.zeros((1,), dtype=torch.int32, device=self.device)
+            self._tmp_bmp = torch.empty((self.units, COMPRESS_CHUNK * 2), dtype=torch.int64, device=self.device)
+            self._tmp_cnt = torch.empty((self.units, COMPRESS_CHUNK * 2), dtype=torch.int32, device=self.device)
+        self.comp_len = 0
+        self.win_len = 0
+        self._ws = None
+        self._ws_bytes = 0
+        self._plan_cache = {}
+        # staging capacity for one 64-token block of nonzeros: kept + pad + slack for ties, in KB
+        def slot_kb(s):
+            kept = HEAD_DIM - prune_rank(s) + 1
+            return min(16, max(1, math.ceil(64 * (kept + 8 + 8) * 2 / 1024)))
+        self.slot_kb = max(slot_kb(k_sparsity), slot_kb(v_sparsity))
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def kv_seq_len(self) -> int:
+        return self.comp_len + self.win_len
+
+    # ------------------------------------------------------------------ compression
+    def _compress_rows(self, stream: _Stream, x: torch.Tensor, layout: int, sparsity: float):
+        """Prune + compress x [units, M, 128] and append it at token offset self.comp_len."""
+        units, m, _ = x.shape
+        tile_off = self.comp_len * 2
+        if m * 2 > self._tmp_bmp.shape[1]:
+            bmp_tmp = torch.empty((units, m * 2), dtype=torch.int64, device=self.device)
+            cnt_tmp = torch.empty((units, m * 2), dtype=torch.int32, device=self.device)
+        else:
+            bmp_tmp = self._tmp_bmp[:, : m * 2] if m * 2 == self._tmp_bmp.shape[1] else torch.empty(
+                (units, m * 2), dtype=torch.int64, device=self.device)
+            cnt_tmp = self._tmp_cnt[:, : m * 2] if m * 2 == self._tmp_cnt.shape[1] else torch.empty(
+                (units, m * 2), dtype=torch.int32, device=self.device)
+        compress_into(x, layout, prune_rank(sparsity), bmp_tmp, cnt_tmp, stream.idx, stream.cap_tiles + 1, tile_off, None)
+        pack_into(x, layout, bmp_tmp, stream.idx, stream.cap_tiles + 1, tile_off, stream.head_base, stream.nz,
+                  stream.head_capacity, self.overflow)
+        stream.bmp[:, tile_off: tile_off + m * 2].copy_(bmp_tmp)
+
+    def prefill(self, key_states: torch.Tensor, value_states: torch.Tensor):
+        """key/value_states: fp16 [B, Hkv, T, 128] (post-RoPE).  llama_mustafar_kernel.py:416-442."""
+        b, h, t, d = key_states.shape
+        assert (b, h, d) == (self.batch, self.kv_heads, HEAD_DIM) and t <= self.cap_tokens
+        L = compressed_length(t, self.residual_length)
+        self.comp_len = 0
+        with torch.cuda.device(self.device):
+            if L > 0:
+                self._compress_rows(self.k, key_states[:, :, :L].reshape(self.units, L, d).contiguous(), _lib.LAYOUT_KEY,
+                                    self.k_sparsity)
+                self._compress_rows(self.v, value_states[:, :, :L].reshape(self.units, L, d).contiguous(),
+                                    _lib.LAYOUT_VALUE, self.v_sparsity)
+            self.comp_len = L
+            lw = t - L
+            assert lw <= self.win_cap
+            self.k_win[:, :lw].copy_(key_states[:, :, L:].reshape(self.units, lw, d))
+            self.v_win[:, :lw].copy_(value_states[:, :, L:].reshape(self.units, lw, d))
+            self.win_len = lw
+
+    def append(self, key_states: torch.Tensor, value_states: torch.Tensor):
+        """Append the new token's k/v rows [B, Hkv, 1, 128] to the dense window (`:270`, `:309`)."""
+        assert self.win_len < self.win_cap
+        k = key_states.reshape(self.units, HEAD_DIM)
+        v = value_states.reshape(self.units, HEAD_DIM)
+        if not k.is_contiguous():
+            k = k.contiguous()
+        if not v.is_contiguous():
+            v = v.contiguous()
+        lib = _lib.load()
+        _lib.check(lib.mfb200_window_append(self.k_win.data_ptr(), self.v_win.data_ptr(), self.win_cap * HEAD_DIM,
+                                            k.data_ptr(), v.data_ptr(), self.units, self.win_len, _lib.stream_ptr()),
+                   "mfb200_window_append")
+        self.win_len += 1
+
+    def maybe_compress(self) -> bool:
+        """`if (kv_seq_len - residual_length - compressed_length) % 256 == 0` — llama_mustafar_kernel.py:324-398."""
+        if self.win_len - self.residual_length != COMPRESS_CHUNK:
+            return False
+        assert self.comp_len + COMPRESS_CHUNK <= self.cap_tokens, "cache capacity exceeded"
+        with torch.cuda.device(self.device):
+            self._compress_rows(self.k, self.k_win[:, :COMPRESS_CHUNK].contiguous(), _lib.LAYOUT_KEY, self.k_sparsity)
+            self._compress_rows(self.v, self.v_win[:, :COMPRESS_CHUNK].contiguous(), _lib.LAYOUT_VALUE, self.v_sparsity)
+            rest = self.win_len - COMPRESS_CHUNK
+            self.k_win[:, :rest].copy_(self.k_win[:, COMPRESS_CHUNK: self.win_len].clone())
+            self.v_win[:, :rest].copy_(self.v_win[:, COMPRESS_CHUNK: self.win_len].clone())
+        self.comp_len += COMPRESS_CHUNK
+        self.win_len = rest
+        return True
+
+    def check_overflow(self):
+        """Host-syncing check of the slab overflow flag (only meaningful with nz_halves_per_token < 128)."""
+        if int(self.overflow.item()) != 0:
+            raise RuntimeError("MustafarKVCache: packed-nonzero slab overflow; raise nz_halves_per_token")
+
+    # ------------------------------------------------------------------ attention
+    def _plan(self):
+        key = (self.comp_len, self.win_len)
+        hit = self._plan_cache.get(key)
+        if hit is not None:
+            return hit
+        lib = _lib.load()
+        ws, cb = C.c_size_t(0), C.c_size_t(0)
+        with torch.cuda.device(self.device):
+            n_split = _lib.check(lib.mfb200_decode_plan(self.batch, self.kv_heads, self.groups, self.comp_len,
+                                                        self.win_len, 0, C.byref(ws), C.byref(cb)), "mfb200_decode_plan")
+        if len(self._plan_cache) > 4096:
+            self._plan_cache.clear()
+        self._plan_cache[key] = (n_split, ws.value)
+        return n_split, ws.value
+
+    def make_params(self, q: torch.Tensor, out: torch.Tensor, mask: Optional[torch.Tensor] = None) -> _lib.DecodeParams:
+        n_split, ws_bytes = self._plan()
+        if self._ws is None or self._ws_bytes < ws_bytes:
+            with torch.cuda.device(self.device):
+                self._ws = torch.zeros((max(ws_bytes, 1 << 20),), dtype=torch.uint8, device=self.device)
+            self._ws_bytes = self._ws.numel()
+        p = _lib.DecodeParams()
+        p.batch, p.kv_heads, p.groups = self.batch, self.kv_heads, self.groups
+        p.comp_len, p.win_len = self.comp_len, self.win_len
+        p.flags = _lib.F_REF_SCORE_ROUNDING if self.ref_score_rounding else 0
+        p.score_div = math.sqrt(HEAD_DIM)
+        p.n_split = n_split
+        p.slot_kb = self.slot_kb
+        p.q, p.out = q.data_ptr(), out.data_ptr()
+        p.k_bmp, p.k_idx, p.k_nz, p.k_nz_off = self.k.bmp.data_ptr(), self.k.idx.data_ptr(), self.k.nz.data_ptr(), self.k.nz_off.data_ptr()
+        p.v_bmp, p.v_idx, p.v_nz, p.v_nz_off = self.v.bmp.data_ptr(), self.v.idx.data_ptr(), self.v.nz.data_ptr(), self.v.nz_off.data_ptr()
+        p.bmp_stride, p.idx_stride = self.k.cap_tiles, self.k.cap_tiles + 1
+        p.k_win, p.v_win, p.win_stride = self.k_win.data_ptr(), self.v_win.data_ptr(), self.win_cap * HEAD_DIM
+        if mask is not None:
+            p.mask, p.mask_stride = mask.data_ptr(), mask.stride(0)
+        else:
+            p.mask, p.mask_stride = None, 0
+        p.workspace = self._ws.data_ptr()
+        return p
+
+    def attend(self, query_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """query_states fp16 [B, Hq, 1, 128] -> attention output fp16 [B, Hq, 1, 128].
+
+        attention_mask: HF additive mask [B, 1, 1, kv_seq_len] (llama_mustafar_kernel.py:293-301) or None.
+        """
+        b, hq, ql, d = query_states.shape
+        if not query_states.is_cuda or query_states.dtype != torch.float16:
+            raise RuntimeError("sparse_decode_attention: query must be a float16 CUDA tensor (no CPU fallback)")
+        assert ql == 1 and d == HEAD_DIM and b == self.batch and hq == self.kv_heads * self.groups
+        q = query_states.reshape(b, hq, d)
+        if not q.is_contiguous():
+            q = q.contiguous()
+        mask2d = None
+        if attention_mask is not None:
+            if attention_mask.size() != (b, 1, 1, self.kv_seq_len):
+                raise ValueError(f"Attention mask should be of size {(b, 1, 1, self.kv_seq_len)}, but is {attention_mask.size()}")
+            mask2d = attention_mask.reshape(b, self.kv_seq_len).to(torch.float16).contiguous()
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty((b, hq, 1, d), dtype=torch.float16, device=self.device)
+            p = self.make_params(q, out, mask2d)
+            _lib.check(_lib.load().mfb200_sparse_decode_attention(C.byref(p), _lib.stream_ptr()),
+                       "mfb200_sparse_decode_attention")
+        return out
+
+    def decode_step(self, query_states, key_states, value_states, attention_mask=None):
+        """One reference decode step of the attention block: append, attend, periodic compression."""
+        self.append(key_states, value_states)
+        out = self.attend(query_states, attention_mask)
+        self.maybe_compress()
+        return out
+
+    # ------------------------------------------------------------------ interop with the reference-shaped ops
+    def as_reference_tuple(self):
+        """(k_compressed, k_local_window, v_compressed, v_local_window, compressed_length, kv_seq_len) with the
+        reference's exact container shapes (llama_mustafar_kernel.py:332, :337, :445) — copies, for interop/tests."""
+        L = self.comp_len
+
+        def one(st: _Stream):
+            if L == 0:
+                return None
+            tiles = L * 2
+            bmp = st.bmp[:, :tiles].contiguous()
+            idx = st.idx[:, : tiles + 1].contiguous()
+            tot = (idx[:, -1].to(torch.int64) * 2).cpu().tolist()
+            nz = [st.nz[u * st.head_capacity: u * st.head_capacity + tot[u]].clone() for u in range(self.units)]
+            t4 = idx[:, -1].to(torch.int64) // 4
+            off = (torch.cumsum(t4, 0) - t4).to(torch.int32)
+            return [bmp, idx, nz, off]
+
+        kw = self.k_win[:, : self.win_len].reshape(self.batch, self.kv_heads, self.win_len, HEAD_DIM).clone()
+        vw = self.v_win[:, : self.win_len].reshape(self.batch, self.kv_heads, self.win_len, HEAD_DIM).clone()
+        return one(self.k), kw, one(self.v), vw, L, self.kv_seq_len
+
+    def compressed_bytes(self):
+        """(algorithmic bytes read by one attend(), idx excluded) — SURVEY.md §8(d).  Host-syncing."""
+        tiles = self.comp_len * 2
+        bmp = 2 * self.units * tiles * 8
+        nz = 0
+        if tiles:
+            nz = 4 * int(self.k.idx[:, tiles].to(torch.int64).sum().item() + self.v.idx[:, tiles].to(torch.int64).sum().item())
+        win = self.units * self.win_len * HEAD_DIM * 2 * 2
+        qo = self.batch * self.kv_heads * self.groups * HEAD_DIM * 2 * 2
+        return bmp + nz + win + qo
+
+
+def mustafar_sparse_decode_attention(query_states: torch.Tensor, cache: MustafarKVCache,
+                                     attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Functional form of `MustafarKVCache.attend` (the fused replacement of llama_mustafar_kernel.py:268-320)."""
+    return cache.attend(query_states, attention_mask)

@@ -1,0 +1,304 @@
+// prune_compress.cu — per-token magnitude pruning and bitmap/packed-nonzero compression.
+//
+// Replaces (paths relative to /root/reference):
+//   models/llama_mustafar_kernel.py:77-153   dh_prune_key / dh_prune_value   (torch.kthvalue + mask)
+//   kernel/compression.py:9-115              calculate_bitmap_{key,value}_batched (Triton)
+//   kernel/compression.py:118-247            compress_{key,value}_batched         (Triton)
+//   kernel/compression.py:294-304            cumsum/cat glue
+//
+// Design (B200): one CTA owns one 64-token block of one head.  The block (64 x 128 fp16 = 16 KB) is
+// read once with 8-byte coalesced loads (a warp reads one 256-byte token row), optionally pruned in
+// registers by a warp-level radix select on the 15-bit magnitudes, and parked in shared memory with
+// a 65-word row pitch so that both the row-wise (V) and the column-wise (K) tile reads are free of
+// bank conflicts.  Bitmap words come from __ballot_sync + __brev (MSB = element 0), ranks from
+// __popc of the ballot below the lane.  Packed tiles are assembled in a per-warp staging line and
+// leave as one contiguous (<=128 B) store per tile.
+#include "common.cuh"
+
+namespace mfb {
+
+constexpr int kPitch = kHeadDim + 2;  // halves; 65 words -> conflict-free column reads
+constexpr int kCompressThreads = 256;
+
+// k-th smallest of the 128 magnitudes held 4 per lane (15-bit integer keys), k in [1,128].
+// Greedy MSB-first construction of the largest T with count(key < T) < k  ==  the k-th smallest.
+__device__ __forceinline__ uint32_t warp_kth_smallest(const uint32_t (&m)[4], int k) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int bit = 14; bit >= 0; --bit) {
+        const uint32_t cand = t | (1u << bit);
+        uint32_t c = (m[0] < cand) + (m[1] < cand) + (m[2] < cand) + (m[3] < cand);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c < static_cast<uint32_t>(k)) t = cand;
+    }
+    return t;
+}
+
+// Applies  x * (|x| >= thr)  to 4 halves packed in a uint2; dropped entries keep their sign bit
+// (fp16 x * 0 = +-0), exactly what `key_states_flat * mask` produces.
+__device__ __forceinline__ uint2 prune4(uint2 v, int k) {
+    uint32_t m[4] = {v.x & 0x7fffu, (v.x >> 16) & 0x7fffu, v.y & 0x7fffu, (v.y >> 16) & 0x7fffu};
+    const uint32_t thr = warp_kth_smallest(m, k);
+    uint32_t keep_lo = (m[0] >= thr ? 0xffffu : 0x8000u) | (m[1] >= thr ? 0xffff0000u : 0x80000000u);
+    uint32_t keep_hi = (m[2] >= thr ? 0xffffu : 0x8000u) | (m[3] >= thr ? 0xffff0000u : 0x80000000u);
+    return make_uint2(v.x & keep_lo, v.y & keep_hi);
+}
+
+__global__ void __launch_bounds__(256) prune_rows_kernel(const uint2* __restrict__ x, uint2* __restrict__ y,
+                                                         int64_t rows, int k) {
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const uint32_t lane = lane_id();
+    uint2 v = x[row * 32 + lane];
+    y[row * 32 + lane] = prune4(v, k);
+}
+
+// Loads one 64-token block of head h into smem (pitch kPitch), pruning on the fly if prune_k > 0.
+__device__ __forceinline__ void load_block(const __half* __restrict__ x, int64_t tokens, int64_t h, int tb,
+                                           int prune_k, uint16_t* tile) {
+    const uint32_t lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const uint2* src = reinterpret_cast<const uint2*>(x + (h * tokens + static_cast<int64_t>(tb) * 64) * kHeadDim);
+    uint2 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ldg_stream_v2(src + (warp * 8 + i) * 32 + lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (prune_k > 0) v[i] = prune4(v[i], prune_k);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tile + (warp * 8 + i) * kPitch + 4 * lane);
+        dst[0] = v[i].x;
+        dst[1] = v[i].y;
+    }
+}
+
+// element (tile-local index e in {lane, lane+32}) of tile `tl` (0..127 inside the block)
+template <int LAYOUT>
+__device__ __forceinline__ void tile_elems(const uint16_t* tile, int tl, uint32_t lane, uint32_t& e0, uint32_t& e1) {
+    if (LAYOUT == MFB200_LAYOUT_KEY) {  // tile = channel tl, elements = tokens
+        e0 = tile[lane * kPitch + tl];
+        e1 = tile[(lane + 32) * kPitch + tl];
+    } else {  // tile = (half = tl/64, token = tl%64), elements = channels of that half
+        const int r = tl & 63, hf = tl >> 6;
+        e0 = tile[r * kPitch + hf * 64 + lane];
+        e1 = tile[r * kPitch + hf * 64 + 32 + lane];
+    }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kCompressThreads)
+compress_count_kernel(const __half* __restrict__ x, int64_t tokens, int prune_k, int64_t* __restrict__ bitmaps,
+                      int32_t* __restrict__ counts) {
+    __shared__ __align__(16) uint16_t tile[64 * kPitch];
+    const int64_t h = blockIdx.y;
+    const int tb = blockIdx.x;
+    load_block(x, tokens, h, tb, prune_k, tile);
+    __syncthreads();
+    const uint32_t lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    uint32_t my_hi = 0, my_lo = 0;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        uint32_t e0, e1;
+        tile_elems<LAYOUT>(tile, warp * 16 + i, lane, e0, e1);
+        const uint32_t hi = __brev(__ballot_sync(0xffffffffu, (e0 & 0x7fffu) != 0));
+        const uint32_t lo = __brev(__ballot_sync(0xffffffffu, (e1 & 0x7fffu) != 0));
+        if (lane == static_cast<uint32_t>(i)) {
+            my_hi = hi;
+            my_lo = lo;
+        }
+    }
+    if (lane < 16) {
+        const int64_t t = h * (tokens * 2) + static_cast<int64_t>(tb) * 128 + warp * 16 + lane;
+        bitmaps[t] = static_cast<int64_t>((static_cast<uint64_t>(my_hi) << 32) | my_lo);
+        counts[t] = ((__popc(my_hi) + __popc(my_lo) + 7) & ~7) >> 1;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+compress_scan_kernel(const int32_t* __restrict__ counts, int64_t tiles, int32_t* __restrict__ accum,
+                     int64_t accum_stride, int64_t tile_offset, int32_t* __restrict__ head_total) {
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t carry_s;
+    const int64_t h = blockIdx.x;
+    const int32_t* c = counts + h * tiles;
+    int32_t* a = accum + h * accum_stride + tile_offset;
+    const uint32_t lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    int32_t carry = 0;
+    if (tile_offset > 0) carry = a[0];
+    else if (threadIdx.x == 0) a[0] = 0;
+    for (int64_t base = 0; base < tiles; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        int32_t v = (i < tiles) ? c[i] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t n = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= static_cast<uint32_t>(o)) v += n;
+        }
+        if (lane == 31) warp_tot[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int32_t w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int32_t n = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= static_cast<uint32_t>(o)) w += n;
+            }
+            warp_tot[lane] = w;  // inclusive over warps
+            if (lane == 31) carry_s = w;
+        }
+        __syncthreads();
+        const int32_t prev = (warp > 0) ? warp_tot[warp - 1] : 0;
+        if (i < tiles) a[i + 1] = carry + prev + v;
+        carry += carry_s;
+        __syncthreads();
+    }
+    if (head_total != nullptr && threadIdx.x == 0) head_total[h] = carry;
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kCompressThreads)
+compress_pack_kernel(const __half* __restrict__ x, int64_t tokens, const int64_t* __restrict__ bitmaps,
+                     const int32_t* __restrict__ accum, int64_t accum_stride, int64_t tile_offset,
+                     const int64_t* __restrict__ head_base, __half* __restrict__ packed, int64_t head_capacity,
+                     int32_t* __restrict__ overflow) {
+    __shared__ __align__(16) uint16_t tile[64 * kPitch];
+    __shared__ __align__(16) uint16_t stage[8][64];
+    const int64_t h = blockIdx.y;
+    const int tb = blockIdx.x;
+    load_block(x, tokens, h, tb, /*prune_k=*/0, tile);
+    __syncthreads();
+    const uint32_t lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const uint32_t above = lane == 0 ? 0u : (0xffffffffu << (32 - lane));  // bits of elements before mine
+    const uint32_t mybit = 0x80000000u >> lane;
+    const int64_t tile0 = static_cast<int64_t>(tb) * 128 + warp * 16;
+    // one coalesced read of this warp's 16 bitmaps and 16 offsets
+    uint64_t bm_l = 0;
+    int32_t off_l = 0;
+    if (lane < 16) {
+        bm_l = static_cast<uint64_t>(bitmaps[h * (tokens * 2) + tile0 + lane]);
+        off_l = accum[h * accum_stride + tile_offset + tile0 + lane];
+    }
+    uint16_t* base = reinterpret_cast<uint16_t*>(packed) + head_base[h];
+    uint32_t* st32 = reinterpret_cast<uint32_t*>(stage[warp]);
+#pragma unroll 2
+    for (int i = 0; i < 16; ++i) {
+        const uint64_t bm = __shfl_sync(0xffffffffu, bm_l, i);
+        const int32_t off = __shfl_sync(0xffffffffu, off_l, i);
+        const uint32_t hi = static_cast<uint32_t>(bm >> 32), lo = static_cast<uint32_t>(bm);
+        uint32_t e0, e1;
+        tile_elems<LAYOUT>(tile, warp * 16 + i, lane, e0, e1);
+        st32[lane] = 0;
+        __syncwarp();
+        const uint32_t pc_hi = __popc(hi);
+        if (hi & mybit) stage[warp][__popc(hi & above)] = static_cast<uint16_t>(e0);
+        if (lo & mybit) stage[warp][pc_hi + __popc(lo & above)] = static_cast<uint16_t>(e1);
+        __syncwarp();
+        const uint32_t n_pad = (pc_hi + __popc(lo) + 7u) & ~7u;
+        if (head_capacity > 0 && 2 * static_cast<int64_t>(off) + n_pad > head_capacity) {
+            if (lane == 0 && overflow != nullptr) atomicExch(overflow, 1);
+        } else if (2 * lane < n_pad) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(base + 2 * static_cast<int64_t>(off));
+            dst[lane] = st32[lane];
+        }
+        __syncwarp();
+    }
+}
+
+// ---- window append: win[u, pos, :] = row[u, :] (K and V in one launch) -------------------------
+__global__ void __launch_bounds__(256)
+window_append_kernel(uint4* __restrict__ k_win, uint4* __restrict__ v_win, int64_t win_stride_v4,
+                     const uint4* __restrict__ k_row, const uint4* __restrict__ v_row, int64_t units, int64_t pos) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // 16 uint4 per row
+    if (i >= units * 16) return;
+    const int64_t u = i >> 4, j = i & 15;
+    k_win[u * win_stride_v4 + pos * 16 + j] = k_row[i];
+    v_win[u * win_stride_v4 + pos * 16 + j] = v_row[i];
+}
+
+}  // namespace mfb
+
+using namespace mfb;
+
+extern "C" int mfb200_prune_rows(const void* x, void* y, int64_t rows, int k, mfb200_stream_t stream) {
+    MFB_REQUIRE(x && y, "prune_rows: null pointer");
+    MFB_REQUIRE(k >= 1 && k <= kHeadDim, "prune_rows: k=%d out of [1,128]", k);
+    MFB_REQUIRE(rows >= 0, "prune_rows: rows < 0");
+    MFB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
+                "prune_rows: pointers must be 8-byte aligned");
+    if (rows == 0) return MFB200_OK;
+    const int64_t grid = (rows + 7) / 8;
+    prune_rows_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint2*>(x), static_cast<uint2*>(y), rows, k);
+    return launch_status("prune_rows_kernel");
+}
+
+extern "C" int mfb200_compress_count(const void* x, int64_t heads, int64_t tokens, int layout, int prune_k,
+                                     int64_t* bitmaps, int32_t* counts, mfb200_stream_t stream) {
+    MFB_REQUIRE(x && bitmaps && counts, "compress_count: null pointer");
+    MFB_REQUIRE(tokens % 64 == 0 && tokens >= 0, "compress_count: tokens=%lld must be a multiple of 64",
+                static_cast<long long>(tokens));
+    MFB_REQUIRE(layout == MFB200_LAYOUT_KEY || layout == MFB200_LAYOUT_VALUE, "compress_count: bad layout %d", layout);
+    MFB_REQUIRE(prune_k >= 0 && prune_k <= kHeadDim, "compress_count: prune_k=%d out of [0,128]", prune_k);
+    MFB_REQUIRE(heads >= 0 && heads <= 65535, "compress_count: heads=%lld out of range", static_cast<long long>(heads));
+    MFB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0, "compress_count: x must be 8-byte aligned");
+    if (heads == 0 || tokens == 0) return MFB200_OK;
+    dim3 grid(static_cast<unsigned>(tokens / 64), static_cast<unsigned>(heads));
+    auto s = static_cast<cudaStream_t>(stream);
+    if (layout == MFB200_LAYOUT_KEY)
+        compress_count_kernel<MFB200_LAYOUT_KEY><<<grid, kCompressThreads, 0, s>>>(static_cast<const __half*>(x), tokens,
+                                                                                     prune_k, bitmaps, counts);
+    else
+        compress_count_kernel<MFB200_LAYOUT_VALUE><<<grid, kCompressThreads, 0, s>>>(static_cast<const __half*>(x),
+                                                                                       tokens, prune_k, bitmaps, counts);
+    return launch_status("compress_count_kernel");
+}
+
+extern "C" int mfb200_compress_scan(const int32_t* counts, int64_t heads, int64_t tiles, int32_t* accum,
+                                    int64_t accum_stride, int64_t tile_offset, int32_t* head_total,
+                                    mfb200_stream_t stream) {
+    MFB_REQUIRE(counts && accum, "compress_scan: null pointer");
+    MFB_REQUIRE(heads >= 0 && tiles >= 0 && tile_offset >= 0, "compress_scan: negative size");
+    MFB_REQUIRE(accum_stride >= tile_offset + tiles + 1, "compress_scan: accum_stride too small");
+    if (heads == 0) return MFB200_OK;
+    compress_scan_kernel<<<static_cast<unsigned>(heads), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+        counts, tiles, accum, accum_stride, tile_offset, head_total);
+    return launch_status("compress_scan_kernel");
+}
+
+extern "C" int mfb200_compress_pack(const void* x, int64_t heads, int64_t tokens, int layout, const int64_t* bitmaps,
+                                    const int32_t* accum, int64_t accum_stride, int64_t tile_offset,
+                                    const int64_t* head_base, void* packed, int64_t head_capacity, int32_t* overflow,
+                                    mfb200_stream_t stream) {
+    MFB_REQUIRE(x && bitmaps && accum && head_base && packed, "compress_pack: null pointer");
+    MFB_REQUIRE(tokens % 64 == 0 && tokens >= 0, "compress_pack: tokens must be a multiple of 64");
+    MFB_REQUIRE(layout == MFB200_LAYOUT_KEY || layout == MFB200_LAYOUT_VALUE, "compress_pack: bad layout %d", layout);
+    MFB_REQUIRE(heads >= 0 && heads <= 65535, "compress_pack: heads out of range");
+    MFB_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "compress_pack: packed must be 16-byte aligned");
+    if (heads == 0 || tokens == 0) return MFB200_OK;
+    dim3 grid(static_cast<unsigned>(tokens / 64), static_cast<unsigned>(heads));
+    auto s = static_cast<cudaStream_t>(stream);
+    if (layout == MFB200_LAYOUT_KEY)
+        compress_pack_kernel<MFB200_LAYOUT_KEY><<<grid, kCompressThreads, 0, s>>>(
+            static_cast<const __half*>(x), tokens, bitmaps, accum, accum_stride, tile_offset, head_base,
+            static_cast<__half*>(packed), head_capacity, overflow);
+    else
+        compress_pack_kernel<MFB200_LAYOUT_VALUE><<<grid, kCompressThreads, 0, s>>>(
+            static_cast<const __half*>(x), tokens, bitmaps, accum, accum_stride, tile_offset, head_base,
+            static_cast<__half*>(packed), head_capacity, overflow);
+    return launch_status("compress_pack_kernel");
+}
+
+extern "C" int mfb200_window_append(void* k_win, void* v_win, int64_t win_stride, const void* k_row,
+                                    const void* v_row, int64_t units, int64_t pos, mfb200_stream_t stream) {
+    MFB_REQUIRE(k_win && v_win && k_row && v_row, "window_append: null pointer");
+    MFB_REQUIRE(win_stride % 8 == 0 && pos >= 0 && (pos + 1) * kHeadDim <= win_stride,
+                "window_append: pos=%lld outside the window capacity", static_cast<long long>(pos));
+    if (units == 0) return MFB200_OK;
+    const int64_t n = units * 16;
+    window_append_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<uint4*>(k_win), static_cast<uint4*>(v_win), win_stride / 8, static_cast<const uint4*>(k_row),
+        static_cast<const uint4*>(v_row), units, pos);
+    return launch_status("window_append_kernel");
+}

@@ -1,0 +1,81 @@
+// ubench.cu — instruction-throughput probe for the design of the tile decoder (sm_100a).
+// Reports warp-instructions per clock per SM for the handful of ops the decode loop is made of.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define ITERS 4096
+
+template <int OP>
+__global__ void k(uint32_t* out, uint32_t seed) {
+    uint32_t a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = seed + threadIdx.x * 8 + i;
+    __shared__ uint32_t sm[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) sm[i] = i * 2654435761u;
+    __syncthreads();
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (OP == 0) a[i] = __popc(a[i]) + seed;                     // POPC (+IADD)
+            if (OP == 1) a[i] = __clz(a[i]) + seed;                      // FLO
+            if (OP == 2) a[i] = __brev(a[i]) + seed;                     // BREV
+            if (OP == 3) a[i] = __shfl_xor_sync(0xffffffffu, a[i], 1);   // SHFL
+            if (OP == 4) a[i] = sm[(a[i] >> 7) & 2047] ;                 // LDS.32 random
+            if (OP == 5) a[i] = (a[i] & seed) + it;                      // LOP+IADD
+            if (OP == 6) a[i] = a[i] * seed + it;                        // IMAD
+            if (OP == 7) { float f = __uint_as_float(a[i]); f = fmaf(f, 1.0001f, 0.5f); a[i] = __float_as_uint(f); }  // FFMA
+            if (OP == 8) a[i] = ((const uint16_t*)sm)[(a[i] >> 7) & 4095] + seed;  // LDS.U16 random
+            if (OP == 9) a[i] = __ballot_sync(0xffffffffu, a[i] & 1) + a[i];  // VOTE
+            if (OP == 10) a[i] = __reduce_add_sync(0xffffffffu, a[i]);   // REDUX
+            if (OP == 11) a[i] = (a[i] & 1) ? a[i] >> 1 : seed;           // SEL-ish
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+template <int OP>
+void run(const char* name, int extra_ops) {
+    int sms;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int clk;
+    cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    uint32_t* out;
+    const int threads = 512, blocks = sms * 4;
+    cudaMalloc(&out, sizeof(uint32_t) * threads * blocks);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k<OP><<<blocks, threads>>>(out, 12345);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    k<OP><<<blocks, threads>>>(out, 12345);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double warp_instr = (double)blocks * (threads / 32) * ITERS * 8;
+    double cycles = ms * 1e-3 * clk * 1e3;
+    printf("%-22s %8.3f ms  %6.2f warp-iters/clk/SM at nominal %d MHz (each iter = op + %d helper)\n", name, ms,
+           warp_instr / cycles / sms, clk / 1000, extra_ops);
+    cudaFree(out);
+}
+
+int main() {
+    run<0>("popc+iadd", 1);
+    run<1>("flo(clz)+iadd", 1);
+    run<2>("brev+iadd", 1);
+    run<3>("shfl", 0);
+    run<4>("lds.32 random", 2);
+    run<5>("lop+iadd", 1);
+    run<6>("imad", 0);
+    run<7>("ffma", 0);
+    run<8>("lds.u16 random+iadd", 3);
+    run<9>("vote+lop+iadd", 2);
+    run<10>("redux.add", 0);
+    run<11>("sel-ish", 2);
+    return 0;
+}
