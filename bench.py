@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — sparse-KV decode attention (the Mustafar hot path) on B200.
+
+Workload (BASELINE.json configs[1], attention path only): Llama-2-7B KV geometry — 32 layers x 32 KV
+heads x 128, MHA — batch 1 per GPU, 4096-token context (compressed length 3840 + dense window 256 at
+the first timed step, growing by one token per step, compression every 256 tokens as in
+models/llama_mustafar_kernel.py:324), K/V sparsity 0.5/0.5.  One "step" = one decode step of the
+attention path over all 32 layers: append the new token's K/V row to the window and run the fused
+sparse decode attention.  Total KV bytes touched per step ≈ 1.4 GB >> L2 (126 MB), so every layer's
+cache is cold when it is read (inputs larger than L2; no explicit flush needed).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1: one process per GPU (torchrun), every rank owns its own sequences (batch-partitioned, no
+collective on the attention path) -> weak scaling, value = all ranks' tokens / max-over-ranks time.
+--impl reference: the reference's masked-dense PyTorch attention
+(models/llama_mustafar_Kt_Mag_Vt_Mag.py:873-874, :963, :974) on the host cores, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LAYERS, HEADS, GROUPS, CTX, GEN, SPARSITY, RESIDUAL = 32, 32, 1, 4096, 1024, 0.5, 32
+METRIC = "sparse-KV decode attention throughput (Llama-2-7B KV geometry, all 32 layers, attention path only)"
+WORKLOAD = ("configs[1]: Llama-2-7B decode attention, batch 1/GPU, 4K context (+ generated), K/V sparsity 0.5/0.5, "
+            "32 layers x 32 heads x 128, bitmap+packed-nonzero cache, residual window 32..288")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", type=int, default=LAYERS, help=argparse.SUPPRESS)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
+        mx = max([int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+def build_pruned_dense(seed, heads, ctx, L, sparsity):
+    """Synthetic K/V of SURVEY §8(d): randn fp16, rows [0, L) pruned with the reference rule (numpy oracle)."""
+    import numpy as np
+    import torch
+    from oracle import mustafar_oracle as O
+    g = torch.Generator().manual_seed(seed)
+    k = torch.randn(1, heads, ctx, 128, generator=g).to(torch.float16).numpy()
+    v = torch.randn(1, heads, ctx, 128, generator=g).to(torch.float16).numpy()
+    k[:, :, :L] = O.prune_rows(k[:, :, :L], sparsity)
+    v[:, :, :L] = O.prune_rows(v[:, :, :L], sparsity)
+    return k, v
+
+
+def cpu_masked_dense(steps, warmup, layers, distinct=4):
+    """The reference's masked-dense decode attention on the host cores (the reported CPU baseline).
+
+    One step = `layers` layer-attentions over pruned-but-dense fp16 K/V [1, 32, 4096, 128]; `distinct`
+    different layer caches (268 MB, larger than any host L3) are cycled."""
+    import math
+    import torch
+    L = ((CTX - RESIDUAL) // 256) * 256
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    caches = []
+    for i in range(distinct):
+        k, v = build_pruned_dense(1000 + i, HEADS, CTX, L, SPARSITY)
+        caches.append((torch.from_numpy(k), torch.from_numpy(v)))
+    q = torch.randn(1, HEADS * GROUPS, 1, 128).to(torch.float16)
+
+    def one(k, v):
+        w = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(128)
+        p = torch.softmax(w, dim=-1, dtype=torch.float32).to(torch.float16)
+        return torch.matmul(p, v)
+
+    def step():
+        for l in range(layers):
+            one(*caches[l % distinct])
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    dt, cores = cpu_masked_dense(steps, max(1, min(args.warmup, 3)), args.layers)
+    val = 1.0 / dt
+    sample = (f"{steps} decode steps x {args.layers} layers of masked-dense fp16 attention "
+              f"(q[1,32,1,128] x K/V[1,32,4096,128]), torch CPU, {cores} threads, 4 distinct layer caches cycled")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "tok/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": max(1, min(args.warmup, 3)), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "inputs larger than L2/L3"},
+            "cpu_baseline": {"value": val, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mustafar_b200 import _lib
+    from mustafar_b200.attention import MustafarKVCache, HEAD_DIM
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    layers = args.layers
+    K, W = args.steps, max(args.warmup, 3)
+    total_steps = 2 * (K + W) + 8
+
+    # ---- build the 32 layer caches at a 4096-token context (prefill compress through the CUDA path) ------
+    torch.manual_seed(42 + rank)
+    caches = []
+    for l in range(layers):
+        k = torch.randn(1, HEADS, CTX, HEAD_DIM, device=dev, dtype=torch.float16)
+        v = torch.randn(1, HEADS, CTX, HEAD_DIM, device=dev, dtype=torch.float16)
+        c = MustafarKVCache(1, HEADS, GROUPS, CTX + max(GEN, total_steps + 300), SPARSITY, SPARSITY, RESIDUAL, device=dev)
+        c.prefill(k, v)
+        # the prompt's last token plays the role of "window incl. the newest token": drop one row so that the
+        # first timed step appends to a 255-row window and attends over L=3840 + Lw=256 = 4096 tokens
+        c.win_len -= 1
+        caches.append(c)
+    del k, v
+    torch.cuda.synchronize()
+    units = HEADS
+
+    # per-step synthetic inputs: [layers, 3(q,k,v), heads, 128]
+    n_in = total_steps
+    dev_in = torch.randn(n_in, layers, 3, HEADS, HEAD_DIM, device=dev, dtype=torch.float16)
+    host_in = torch.randn(n_in, layers, 3, HEADS, HEAD_DIM, dtype=torch.float16).pin_memory()
+    dev_out = torch.empty(layers, HEADS, 1, HEAD_DIM, device=dev, dtype=torch.float16)
+    host_out = torch.empty(layers, HEADS, 1, HEAD_DIM, dtype=torch.float16).pin_memory()
+    stage_in = torch.empty(layers, 3, HEADS, HEAD_DIM, device=dev, dtype=torch.float16)
+    launches = [0]
+
+    def step_device(x, compress=True):
+        """x: device tensor [layers, 3, heads, 128].  append + fused attention for every layer."""
+        for l, c in enumerate(caches):
+            c.append(x[l, 1], x[l, 2])
+            c.attend(x[l, 0].view(1, HEADS, 1, HEAD_DIM), out=dev_out[l:l + 1])
+            launches[0] += 2
+            if compress and c.maybe_compress():
+                launches[0] += 6
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    pos = [0]
+
+    def nxt():
+        pos[0] += 1
+        return pos[0] - 1
+
+    # ---- (1) device-resident throughput -------------------------------------------------------------------
+    for _ in range(W):
+        step_device(dev_in[nxt()])
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches[0] = 0
+    bytes_before = caches[0].compressed_bytes()
+    ms_dev = timed(lambda i: step_device(dev_in[nxt()]), K)
+    gpu_launches = launches[0]
+    clocks = sampler.stop()
+
+    # ---- (2) dominant kernel alone: 32 attends per step at the current state, CUDA events on the launch stream
+    algo_bytes = caches[0].compressed_bytes()
+    q_fix = dev_in[0]
+    params = [c.make_params(q_fix[l, 0].contiguous(), dev_out[l:l + 1]) for l, c in enumerate(caches)]
+    import ctypes as C
+    sp = _lib.stream_ptr()
+    attn = lib.mfb200_sparse_decode_attention
+
+    def attends(_):
+        for p in params:
+            attn(C.byref(p), sp)
+
+    for _ in range(3):
+        attends(0)
+    ms_k = timed(attends, K)
+    us_per_launch = ms_k * 1e3 / (K * layers)
+
+    # ---- (3) end to end through the public API with HOST buffers -----------------------------------------------
+    def step_e2e(_):
+        i = nxt()
+        stage_in.copy_(host_in[i], non_blocking=True)
+        step_device(stage_in)
+        host_out.copy_(dev_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller needs this step's result before the next token
+
+    for _ in range(W):
+        step_e2e(0)
+    ms_e2e = timed(step_e2e, K)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    achieved = algo_bytes / (us_per_launch * 1e-6) / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        dt, cores = cpu_masked_dense(3, 1, layers)
+        cpu = {"value": 1.0 / dt, "unit": "tok/s", "cores": cores, "kind": "port",
+               "sample": f"3 decode steps x {layers} layers masked-dense fp16 attention at T=4096 on torch CPU ({cores} threads)"}
+    h2d = stage_in.numel() * 2
+    d2h = dev_out.numel() * 2
+    line = {
+        "metric": METRIC, "value": world * 1e3 * K / ms_dev, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": world, "layers": layers, "context": CTX,
+                   "l2": "inputs larger than L2 (1.4 GB of KV per step), no flush needed",
+                   "partition": "batch-partitioned across ranks, no collective"},
+        "us_per_layer_step": ms_dev * 1e3 / (K * layers),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "sparse_decode_attn_kernel<1>",
+                     "us_per_launch": us_per_launch, "algorithmic_bytes_per_launch": algo_bytes,
+                     "frac_of_8TBps_spec": achieved / 8000.0,
+                     "how": "32 x K back-to-back launches (one per layer cache, 1.4 GB working set), CUDA events on the launch stream"},
+        "e2e": {"value": world * 1e3 * K / ms_e2e, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": gpu_launches, "clocks": clocks, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
