@@ -188,13 +188,13 @@ def run_ours(args):
     launches = [0]
 
     def step_device(x, compress=True):
-        """x: device tensor [layers, 3, heads, 128].  append + fused attention for every layer."""
+        """x: device tensor [layers, 3, heads, 128].  One fused (append + attention) launch per layer."""
         for l, c in enumerate(caches):
-            c.append(x[l, 1], x[l, 2])
-            c.attend(x[l, 0].view(1, HEADS, 1, HEAD_DIM), out=dev_out[l:l + 1])
-            launches[0] += 2
-            if compress and c.maybe_compress():
-                launches[0] += 6
+            before = c.comp_len
+            c.decode_step(x[l, 0].view(1, HEADS, 1, HEAD_DIM), x[l, 1], x[l, 2], out=dev_out[l:l + 1])
+            launches[0] += 1  # fused append + attention: sparse_decode_attn_kernel
+            if c.comp_len != before:
+                launches[0] += 6  # K and V: compress_count, compress_scan, compress_pack
 
     def timed(fn, n):
         if world > 1:

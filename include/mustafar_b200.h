@@ -136,10 +136,16 @@ typedef struct mfb200_decode_params {
     const int64_t* v_nz_off;
     int64_t bmp_stride; /* in tiles */
     int64_t idx_stride; /* in entries */
-    /* dense window: fp16, row t of unit u at  win + u*win_stride + t*128 */
-    const void* k_win;
-    const void* v_win;
+    /* dense window: fp16, row t of unit u at  win + u*win_stride + t*128 (written only when k_new/v_new
+     * are given) */
+    void* k_win;
+    void* v_win;
     int64_t win_stride; /* halves */
+    /* optional fused append of the step's new token (models/llama_mustafar_kernel.py:270, :309): fp16
+     * [units, 128] rows that the kernel stores at window row win_len-1 (win_len already counts the new
+     * token) and attends to in the same launch; both NULL = the window already holds every row. */
+    const void* k_new;
+    const void* v_new;
     /* optional additive mask, fp16 [B, mask_stride], entry t (0 <= t < L+Lw); NULL = none */
     const void* mask;
     int64_t mask_stride;

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmustafar_b200.so")
+LIB_PATH = os.environ.get("MFB200_LIB", os.path.join(_HERE, "libmustafar_b200.so"))  # override: A/B builds only
 
 ABI_VERSION = 1
 LAYOUT_KEY = 0
@@ -33,6 +33,7 @@ class DecodeParams(C.Structure):
         ("v_bmp", _vp), ("v_idx", _vp), ("v_nz", _vp), ("v_nz_off", _vp),
         ("bmp_stride", _i64), ("idx_stride", _i64),
         ("k_win", _vp), ("v_win", _vp), ("win_stride", _i64),
+        ("k_new", _vp), ("v_new", _vp),
         ("mask", _vp), ("mask_stride", _i64),
         ("workspace", _vp),
     ]

@@ -85,6 +85,9 @@ class MustafarKVCache:
         self._ws = None
         self._ws_bytes = 0
         self._plan_cache = {}
+        self._p = None
+        self._sm_count = 0
+        self._attn = _lib.load().mfb200_sparse_decode_attention
         # staging capacity for one 64-token block of nonzeros: kept + pad + slack for ties, in KB
         def slot_kb(s):
             kept = HEAD_DIM - prune_rank(s) + 1
@@ -176,69 +179,98 @@ class MustafarKVCache:
             return hit
         lib = _lib.load()
         ws, cb = C.c_size_t(0), C.c_size_t(0)
-        with torch.cuda.device(self.device):
-            n_split = _lib.check(lib.mfb200_decode_plan(self.batch, self.kv_heads, self.groups, self.comp_len,
-                                                        self.win_len, 0, C.byref(ws), C.byref(cb)), "mfb200_decode_plan")
+        n_split = _lib.check(lib.mfb200_decode_plan(self.batch, self.kv_heads, self.groups, self.comp_len,
+                                                    self.win_len, self._sm_count, C.byref(ws), C.byref(cb)),
+                             "mfb200_decode_plan")
         if len(self._plan_cache) > 4096:
             self._plan_cache.clear()
         self._plan_cache[key] = (n_split, ws.value)
         return n_split, ws.value
 
-    def make_params(self, q: torch.Tensor, out: torch.Tensor, mask: Optional[torch.Tensor] = None) -> _lib.DecodeParams:
-        n_split, ws_bytes = self._plan()
-        if self._ws is None or self._ws_bytes < ws_bytes:
-            with torch.cuda.device(self.device):
-                self._ws = torch.zeros((max(ws_bytes, 1 << 20),), dtype=torch.uint8, device=self.device)
-            self._ws_bytes = self._ws.numel()
+    def _static_params(self) -> _lib.DecodeParams:
+        """The fields of the C struct that never change for this cache (pointers of the slabs, strides)."""
         p = _lib.DecodeParams()
         p.batch, p.kv_heads, p.groups = self.batch, self.kv_heads, self.groups
-        p.comp_len, p.win_len = self.comp_len, self.win_len
         p.flags = _lib.F_REF_SCORE_ROUNDING if self.ref_score_rounding else 0
         p.score_div = math.sqrt(HEAD_DIM)
-        p.n_split = n_split
         p.slot_kb = self.slot_kb
-        p.q, p.out = q.data_ptr(), out.data_ptr()
         p.k_bmp, p.k_idx, p.k_nz, p.k_nz_off = self.k.bmp.data_ptr(), self.k.idx.data_ptr(), self.k.nz.data_ptr(), self.k.nz_off.data_ptr()
         p.v_bmp, p.v_idx, p.v_nz, p.v_nz_off = self.v.bmp.data_ptr(), self.v.idx.data_ptr(), self.v.nz.data_ptr(), self.v.nz_off.data_ptr()
         p.bmp_stride, p.idx_stride = self.k.cap_tiles, self.k.cap_tiles + 1
         p.k_win, p.v_win, p.win_stride = self.k_win.data_ptr(), self.v_win.data_ptr(), self.win_cap * HEAD_DIM
+        return p
+
+    def make_params(self, q: torch.Tensor, out: torch.Tensor, mask: Optional[torch.Tensor] = None,
+                    k_new: Optional[torch.Tensor] = None, v_new: Optional[torch.Tensor] = None) -> _lib.DecodeParams:
+        """Fills the (cached) C parameter block for one launch at the cache's current lengths.  When k_new/v_new
+        are given, self.win_len must already count the new token."""
+        if self._p is None:
+            self._sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
+            self._p = self._static_params()
+        p = self._p
+        n_split, ws_bytes = self._plan()
+        if self._ws_bytes < ws_bytes:
+            with torch.cuda.device(self.device):
+                self._ws = torch.zeros((max(ws_bytes, 1 << 20),), dtype=torch.uint8, device=self.device)
+            self._ws_bytes = self._ws.numel()
+            p.workspace = self._ws.data_ptr()
+        p.comp_len, p.win_len, p.n_split = self.comp_len, self.win_len, n_split
+        p.q, p.out = q.data_ptr(), out.data_ptr()
+        if k_new is not None:
+            p.k_new, p.v_new = k_new.data_ptr(), v_new.data_ptr()
+        else:
+            p.k_new, p.v_new = None, None
         if mask is not None:
             p.mask, p.mask_stride = mask.data_ptr(), mask.stride(0)
         else:
             p.mask, p.mask_stride = None, 0
-        p.workspace = self._ws.data_ptr()
         return p
+
+    def _check_q(self, query_states):
+        if not query_states.is_cuda or query_states.dtype != torch.float16:
+            raise RuntimeError("sparse_decode_attention: query must be a float16 CUDA tensor (no CPU fallback)")
+        b, hq, ql, d = query_states.shape
+        assert ql == 1 and d == HEAD_DIM and b == self.batch and hq == self.kv_heads * self.groups
+        return query_states if query_states.is_contiguous() else query_states.contiguous()
+
+    def _mask2d(self, attention_mask):
+        if attention_mask is None:
+            return None
+        if attention_mask.size() != (self.batch, 1, 1, self.kv_seq_len):
+            raise ValueError(f"Attention mask should be of size {(self.batch, 1, 1, self.kv_seq_len)}, but is {attention_mask.size()}")
+        return attention_mask.reshape(self.batch, self.kv_seq_len).to(torch.float16).contiguous()
+
+    def _launch(self, p):
+        rc = self._attn(C.byref(p), torch.cuda.current_stream(self.device).cuda_stream)
+        if rc < 0:
+            _lib.check(rc, "mfb200_sparse_decode_attention")
 
     def attend(self, query_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """query_states fp16 [B, Hq, 1, 128] -> attention output fp16 [B, Hq, 1, 128].
+        """query_states fp16 [B, Hq, 1, 128] -> attention output fp16 [B, Hq, 1, 128] over the cache as it is.
 
         attention_mask: HF additive mask [B, 1, 1, kv_seq_len] (llama_mustafar_kernel.py:293-301) or None.
+        The caller's current CUDA device must be the cache's device.
         """
-        b, hq, ql, d = query_states.shape
-        if not query_states.is_cuda or query_states.dtype != torch.float16:
-            raise RuntimeError("sparse_decode_attention: query must be a float16 CUDA tensor (no CPU fallback)")
-        assert ql == 1 and d == HEAD_DIM and b == self.batch and hq == self.kv_heads * self.groups
-        q = query_states.reshape(b, hq, d)
-        if not q.is_contiguous():
-            q = q.contiguous()
-        mask2d = None
-        if attention_mask is not None:
-            if attention_mask.size() != (b, 1, 1, self.kv_seq_len):
-                raise ValueError(f"Attention mask should be of size {(b, 1, 1, self.kv_seq_len)}, but is {attention_mask.size()}")
-            mask2d = attention_mask.reshape(b, self.kv_seq_len).to(torch.float16).contiguous()
-        with torch.cuda.device(self.device):
-            if out is None:
-                out = torch.empty((b, hq, 1, d), dtype=torch.float16, device=self.device)
-            p = self.make_params(q, out, mask2d)
-            _lib.check(_lib.load().mfb200_sparse_decode_attention(C.byref(p), _lib.stream_ptr()),
-                       "mfb200_sparse_decode_attention")
+        q = self._check_q(query_states)
+        if out is None:
+            out = torch.empty_like(q)
+        self._launch(self.make_params(q, out, self._mask2d(attention_mask)))
         return out
 
-    def decode_step(self, query_states, key_states, value_states, attention_mask=None):
-        """One reference decode step of the attention block: append, attend, periodic compression."""
-        self.append(key_states, value_states)
-        out = self.attend(query_states, attention_mask)
+    def decode_step(self, query_states, key_states, value_states, attention_mask=None, out=None):
+        """One reference decode step of the attention block (llama_mustafar_kernel.py:256-398) in ONE launch:
+        the new token's K/V rows [B, Hkv, 1, 128] are appended to the window by the attention kernel itself,
+        which attends over compressed + window (incl. the new token); then the periodic compression."""
+        assert self.win_len < self.win_cap
+        q = self._check_q(query_states)
+        k = key_states if key_states.is_contiguous() else key_states.contiguous()
+        v = value_states if value_states.is_contiguous() else value_states.contiguous()
+        assert k.numel() == self.units * HEAD_DIM and v.numel() == k.numel() and k.dtype == torch.float16
+        if out is None:
+            out = torch.empty_like(q)
+        self.win_len += 1
+        self._launch(self.make_params(q, out, self._mask2d(attention_mask), k, v))
         self.maybe_compress()
         return out
 

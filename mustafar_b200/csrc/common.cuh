@@ -53,8 +53,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    // not volatile: the address always derives from a record loaded after the relevant barrier, so the
+    // data dependence orders it; leaving it schedulable lets ptxas interleave several tiles.
     uint16_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
@@ -100,7 +102,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"  // suspend-time hint: sleep, don't spin
         "@p bra DONE;\n"
         "bra WAIT_LOOP;\n"
         "DONE:\n"

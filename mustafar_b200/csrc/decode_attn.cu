@@ -6,26 +6,40 @@
 // add, and the (never launched) SplitK_Reduction (kernel/csrc/Reduction_Kernel.cuh:26-48).
 //
 // Work decomposition: unit = (sequence, KV head); the compressed length is cut into `n_csplit`
-// contiguous ranges of 64-token blocks, the dense window into ranges of <= 256 tokens; grid =
-// (n_split, units).  Each CTA keeps flash-decoding state (m, l, o) in registers, writes one fp32
-// partial and the last CTA of a unit (atomic ticket) merges the partials -> single launch, no
-// second kernel, graph-capturable.  All G query heads of a KV head are served by the same CTA, so the
-// compressed bytes of a KV head cross HBM once (the reference re-reads them G times,
-// kernel/csrc/SpMM_Kernel.cuh:175).
+// contiguous ranges of 64-token blocks, the dense window into ranges of <= 64 tokens; grid =
+// n_split * units CTAs (compressed splits first).  Each CTA keeps flash-decoding state (m, l, o), writes one fp32 partial and the
+// last CTA of a unit (atomic ticket) merges the partials -> single launch, no second kernel,
+// graph-capturable.  All G query heads of a KV head are served by the same CTA, so the compressed
+// bytes of a KV head cross HBM once (the reference re-reads them G times, SpMM_Kernel.cuh:175).
 //
-// Data path of a compressed split: per 64-token block two pipeline items (K then V), each =
-// 1 KB of bitmaps + the block's contiguous nonzero range.  A single elected thread moves them with
-// cp.async.bulk (TMA engine) into a 4-slot shared-memory ring, completion through mbarrier
-// expect-tx.  Consumers never build a dense tile: see sparse_tile.cuh.
+// A compressed-split CTA is warp-specialised and has NO CTA-wide barrier in its steady state:
+//   warp 9      producer : one lane issues cp.async.bulk (TMA engine) copies of each block's K item and
+//                          V item (1 KB bitmaps + the block's contiguous nonzero range) into two
+//                          shared-memory rings; completion through mbarrier expect-tx.
+//   warps 0-3   K role   : 32 tiles (channels) each -> partial scores of the block's 64 tokens.
+//   warp 8      softmax  : sums the 4 partials, online-softmax update, publishes p[64] and the
+//                          rescale factor.
+//   warps 4-7   V role   : 32 tiles each (one channel half x 32 tokens) -> o accumulators.
+// Every hand-off (slot full/empty, scores full/empty, probabilities full/empty) is an mbarrier, so
+// the K warps run ahead of the V warps by up to two blocks and nobody waits for the slowest warp.
+// Nothing dense is ever rebuilt in shared memory (sparse_tile.cuh).
 #include "sparse_tile.cuh"
 
 namespace mfb {
 
-constexpr int kAttnThreads = 128;
-constexpr int kAttnWarps = 4;
-constexpr int kSlots = 4;
+#ifndef MFB_G1_CTAS
+#define MFB_G1_CTAS 2  // resident CTAs per SM the G=1 kernel is compiled for
+#endif
+constexpr int kTileWarps = 4;                 // per role
+constexpr int kWarpK0 = 0, kWarpV0 = 4, kWarpSoftmax = 8, kWarpProducer = 9;
+constexpr int kAttnWarps = 10;
+constexpr int kAttnThreads = kAttnWarps * 32;  // 320
+constexpr int kWinWarps = 8;                   // warps used by the dense-window path
+constexpr int kWinThreads = kWinWarps * 32;
+constexpr int kChunk = 16;                     // tiles per operand-register chunk
+constexpr int kMaxDepth = 4;
 constexpr int kMaxBlocksPerSplit = 128;
-constexpr int kWinTokensPerSplit = 256;
+constexpr int kWinTokensPerSplit = 64;
 constexpr int kPartStride = 132;  // floats per (split, head): o[128], m, l, pad
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -33,34 +47,60 @@ struct DecodeArgs {
     mfb200_decode_params p;
     int n_csplit;
     int n_wsplit;
-    int slot_nz_bytes;  // capacity of a slot's nonzero area (multiple of 16)
+    int slot_nz_bytes;  // capacity of a slot's nonzero area (multiple of 1024)
+    int depth;          // ring depth per stream (K and V each), 2..4
+};
+
+// barrier indices inside the bars[] array
+struct Bars {
+    enum : int {
+        kFullK = 0,                  // [depth] producer -> K warps
+        kEmptyK = kMaxDepth,         // [depth] K warps -> producer      (count 4)
+        kFullV = 2 * kMaxDepth,      // [depth]
+        kEmptyV = 3 * kMaxDepth,     // [depth]                          (count 4)
+        kScFull = 4 * kMaxDepth,     // [2] K warps -> softmax           (count 4)
+        kScEmpty = kScFull + 2,      // [2] softmax -> K warps           (count 1)
+        kPFull = kScEmpty + 2,       // [2] softmax -> V warps           (count 1)
+        kPEmpty = kPFull + 2,        // [2] V warps -> softmax           (count 4)
+        kCount = kPEmpty + 2
+    };
 };
 
 struct SmemMap {
-    uint32_t slots, bars, rec, qs, spart, ps, segk, segv, total;
+    uint32_t slots_k, slots_v, bars, rec, qs, spart, ps, corr, stat, segk, segv, total;
 };
 
-__host__ __device__ inline SmemMap smem_map(int G, int slot_nz_bytes) {
+__host__ __device__ inline SmemMap smem_map(int G, int slot_nz_bytes, int depth) {
     SmemMap m;
     uint32_t o = 0;
-    m.slots = o;
-    o += kSlots * (1024 + slot_nz_bytes);
+    m.slots_k = o;
+    o += depth * (1024 + slot_nz_bytes);
+    m.slots_v = o;
+    o += depth * (1024 + slot_nz_bytes);
     m.bars = o;
-    o += 64;
-    m.rec = o;
-    o += kAttnWarps * 64 * 8;  // uint2[64] per warp
-    m.qs = o;
-    o += kHeadDim * G * 4;
-    m.spart = o;  // float [2][warps][G][64]; also reused for the final cross-warp reduction
-    o += 2 * kAttnWarps * G * 64 * 4;
-    m.ps = o;  // float [warps][64][G]
-    o += kAttnWarps * 64 * G * 4;
+    o += ((Bars::kCount * 8 + 15) / 16) * 16;
+    m.rec = o;  // uint2 [8 consumer warps][32 tiles][2]
+    o += 2 * kTileWarps * 64 * 8;
+    m.qs = o;  // half [128][G]
+    o += kHeadDim * G * 2;
+    m.spart = o;  // float [2][4 warps][G][64]; reused for the final cross-warp reduction of o
+    o += 2 * kTileWarps * G * 64 * 4;
+    m.ps = o;  // half [2][64][G]
+    o += 2 * 64 * G * 2;
+    m.corr = o;  // float [2][8]
+    o += 2 * 8 * 4;
+    m.stat = o;  // float m[8], l[8]
+    o += 2 * 8 * 4;
     m.segk = o;
     o += (kMaxBlocksPerSplit * 4 + 4) * 4;
     m.segv = o;
     o += (kMaxBlocksPerSplit * 4 + 4) * 4;
     m.total = o;
     return m;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ float ref_round_score(float dot, float div, bool ref_rounding) {
@@ -73,10 +113,10 @@ __device__ __forceinline__ float ref_round_score(float dot, float div, bool ref_
     return dot / div;
 }
 
+// Writes this split's partial (o[G][128] from smem `ored`, m, l) and lets the last CTA of the unit merge.
 template <int G>
 __device__ __forceinline__ void write_partial_and_merge(const DecodeArgs& a, int unit, int split, const float* ored,
-                                                        /* ored: [G][128] in smem, already reduced */
-                                                        const float (&m)[G], const float (&l)[G]) {
+                                                        const float* m, const float* l) {
     const mfb200_decode_params& p = a.p;
     const int tid = threadIdx.x;
     const int n_split = a.n_csplit + a.n_wsplit;
@@ -84,13 +124,10 @@ __device__ __forceinline__ void write_partial_and_merge(const DecodeArgs& a, int
     int* counters = static_cast<int*>(p.workspace);
     float* parts = reinterpret_cast<float*>(static_cast<uint8_t*>(p.workspace) + ((units * 4 + 255) & ~255));
     float* mine = parts + (static_cast<int64_t>(unit) * n_split + split) * G * kPartStride;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        mine[g * kPartStride + tid] = ored[g * 128 + tid];
-        if (tid == 0) {
-            mine[g * kPartStride + 128] = m[g];
-            mine[g * kPartStride + 129] = l[g];
-        }
+    for (int i = tid; i < G * 128; i += kAttnThreads) mine[(i >> 7) * kPartStride + (i & 127)] = ored[i];
+    if (tid < G) {
+        mine[tid * kPartStride + 128] = m[tid];
+        mine[tid * kPartStride + 129] = l[tid];
     }
     __shared__ int s_last;
     __threadfence();
@@ -103,9 +140,8 @@ __device__ __forceinline__ void write_partial_and_merge(const DecodeArgs& a, int
     if (!s_last) return;
     __threadfence();
     const float* up = parts + static_cast<int64_t>(unit) * n_split * G * kPartStride;
-    const int b = unit / p.kv_heads, h = unit % p.kv_heads;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
+    for (int i = tid; i < G * 128; i += kAttnThreads) {
+        const int g = i >> 7, c = i & 127;
         float mx = -INFINITY;
         for (int s = 0; s < n_split; ++s) mx = fmaxf(mx, __ldcg(up + (s * G + g) * kPartStride + 128));
         float den = 0.f, num = 0.f;
@@ -114,42 +150,93 @@ __device__ __forceinline__ void write_partial_and_merge(const DecodeArgs& a, int
             const float ms = __ldcg(ps + 128);
             const float w = (ms == -INFINITY) ? 0.f : exp2f((ms - mx) * kLog2e);
             den += __ldcg(ps + 129) * w;
-            num += __ldcg(ps + tid) * w;
+            num += __ldcg(ps + c) * w;
         }
-        const int64_t qh = (static_cast<int64_t>(b) * p.kv_heads + h) * G + g;
-        static_cast<__half*>(p.out)[qh * kHeadDim + tid] = __float2half_rn(num / den);
+        const int64_t qh = static_cast<int64_t>(unit) * G + g;  // = b*Hq + h*G + g
+        static_cast<__half*>(p.out)[qh * kHeadDim + c] = __float2half_rn(num / den);
     }
     if (tid == 0) counters[unit] = 0;  // ready for the next launch / graph replay
+}
+
+// One chunk of 16 tiles.  `oper` = the per-tile fp16 FMA operands [16][G] in shared memory (q for K
+// tiles, p for V tiles; 16-byte aligned): pulled into registers with 128-bit loads for G <= 4, read
+// with one broadcast 128-bit load per tile for G = 8.
+template <int G, bool NZ_SHARED>
+__device__ __forceinline__ void tiles_chunk(const uint2* rec, const LaneConst& lc, const uint8_t* gbase,
+                                            const __half* oper, float (&acc)[G][2]) {
+    if constexpr (G <= 4) {
+        constexpr int kVec = kChunk * G / 8;  // uint4 loads
+        uint4 wv[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) wv[i] = reinterpret_cast<const uint4*>(oper)[i];
+        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(wv);
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) {
+            const DecodedPair d = decode_pair<NZ_SHARED>(rec + 2 * j, lc, gbase);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int e = j * G + g;
+                const uint16_t w = static_cast<uint16_t>((e & 1) ? (w32[e >> 1] >> 16) : (w32[e >> 1] & 0xffffu));
+                if (d.b0) acc[g][0] = fhfma(d.x, w, acc[g][0]);
+                if (d.b1) acc[g][1] = fhfma(d.y, w, acc[g][1]);
+            }
+        }
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < kChunk; ++j) {
+            const DecodedPair d = decode_pair<NZ_SHARED>(rec + 2 * j, lc, gbase);
+            const uint4 wv = reinterpret_cast<const uint4*>(oper)[j];
+            const uint32_t w32[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const uint16_t w = static_cast<uint16_t>((g & 1) ? (w32[g >> 1] >> 16) : (w32[g >> 1] & 0xffffu));
+                if (d.b0) acc[g][0] = fhfma(d.x, w, acc[g][0]);
+                if (d.b1) acc[g][1] = fhfma(d.y, w, acc[g][1]);
+            }
+        }
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void tiles32(bool nz_shared, const uint2* rec, const LaneConst& lc, const uint8_t* gbase,
+                                        const __half* oper, float (&acc)[G][2]) {
+    if (nz_shared) {
+        tiles_chunk<G, true>(rec, lc, gbase, oper, acc);
+        tiles_chunk<G, true>(rec + 2 * kChunk, lc, gbase, oper + kChunk * G, acc);
+    } else {
+        tiles_chunk<G, false>(rec, lc, gbase, oper, acc);
+        tiles_chunk<G, false>(rec + 2 * kChunk, lc, gbase, oper + kChunk * G, acc);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 template <int G>
 __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* smem, int unit, int split) {
     const mfb200_decode_params& p = a.p;
-    const SmemMap sm = smem_map(G, a.slot_nz_bytes);
+    const int D = a.depth;
+    const SmemMap sm = smem_map(G, a.slot_nz_bytes, D);
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t lane = lane_id();
     const int nblk_total = p.comp_len / kBlockTokens;
     const int blk0 = static_cast<int>(static_cast<int64_t>(split) * nblk_total / a.n_csplit);
     const int blk1 = static_cast<int>(static_cast<int64_t>(split + 1) * nblk_total / a.n_csplit);
     const int nb = blk1 - blk0;
-    const int b = unit / p.kv_heads, h = unit % p.kv_heads;
-    const bool ref_round = (p.flags & MFB200_F_REF_SCORE_ROUNDING) != 0;
+    const int b = unit / p.kv_heads;
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);
-    uint2* rec = reinterpret_cast<uint2*>(smem + sm.rec) + warp * 64;
-    float* qs = reinterpret_cast<float*>(smem + sm.qs);        // [c][G]
-    float* spart = reinterpret_cast<float*>(smem + sm.spart);  // [2][warps][G][64]
-    float* ps = reinterpret_cast<float*>(smem + sm.ps) + warp * 64 * G;  // [64][G]
+    __half* qs = reinterpret_cast<__half*>(smem + sm.qs);      // [c][G]
+    float* spart = reinterpret_cast<float*>(smem + sm.spart);  // [2][4][G][64]
+    __half* ps = reinterpret_cast<__half*>(smem + sm.ps);      // [2][64][G]
+    float* corr = reinterpret_cast<float*>(smem + sm.corr);    // [2][8]
+    float* stat = reinterpret_cast<float*>(smem + sm.stat);    // m[8], l[8]
     uint32_t* segk = reinterpret_cast<uint32_t*>(smem + sm.segk);
     uint32_t* segv = reinterpret_cast<uint32_t*>(smem + sm.segv);
     const uint32_t slot_bytes = 1024u + a.slot_nz_bytes;
 
     // ---- prologue: q -> fp32 smem, 32-tile segment offsets of this split, barriers ---------------
     {
-        const __half* q = static_cast<const __half*>(p.q) + (static_cast<int64_t>(b) * p.kv_heads + h) * G * kHeadDim;
-#pragma unroll
-        for (int g = 0; g < G; ++g) qs[tid * G + g] = __half2float(q[g * kHeadDim + tid]);
+        const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
+        for (int i = tid; i < G * kHeadDim; i += kAttnThreads) qs[(i & 127) * G + (i >> 7)] = q[i];
         const uint32_t* ki = p.k_idx + static_cast<int64_t>(unit) * p.idx_stride + static_cast<int64_t>(blk0) * 128;
         const uint32_t* vi = p.v_idx + static_cast<int64_t>(unit) * p.idx_stride + static_cast<int64_t>(blk0) * 128;
         for (int i = tid; i <= nb * 4; i += kAttnThreads) {
@@ -157,8 +244,18 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             segv[i] = __ldg(vi + i * 32);
         }
         if (tid == 0) {
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s) mbar_init(&bars[s], 1);
+            for (int s = 0; s < kMaxDepth; ++s) {
+                mbar_init(&bars[Bars::kFullK + s], 1);
+                mbar_init(&bars[Bars::kEmptyK + s], kTileWarps);
+                mbar_init(&bars[Bars::kFullV + s], 1);
+                mbar_init(&bars[Bars::kEmptyV + s], kTileWarps);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&bars[Bars::kScFull + s], kTileWarps);
+                mbar_init(&bars[Bars::kScEmpty + s], 1);
+                mbar_init(&bars[Bars::kPFull + s], 1);
+                mbar_init(&bars[Bars::kPEmpty + s], kTileWarps);
+            }
             fence_mbar_init();
         }
     }
@@ -166,209 +263,269 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
 
     const uint8_t* k_nz = static_cast<const uint8_t*>(p.k_nz) + p.k_nz_off[unit] * 16;
     const uint8_t* v_nz = static_cast<const uint8_t*>(p.v_nz) + p.v_nz_off[unit] * 16;
-    const uint64_t* k_bmp = p.k_bmp + static_cast<int64_t>(unit) * p.bmp_stride + static_cast<int64_t>(blk0) * 128;
-    const uint64_t* v_bmp = p.v_bmp + static_cast<int64_t>(unit) * p.bmp_stride + static_cast<int64_t>(blk0) * 128;
-
-    const int n_items = 2 * nb;
-    int issued = 0;
-    auto issue_until = [&](int limit) {  // thread 0 only
-        for (; issued < limit && issued < n_items; ++issued) {
-            const int blk = issued >> 1, is_v = issued & 1, slot = issued & (kSlots - 1);
-            const uint32_t* seg = is_v ? segv : segk;
-            const uint32_t off0 = seg[blk * 4], off1 = seg[blk * 4 + 4];
-            const uint32_t bytes = (off1 - off0) * 4u;
-            const bool fits = bytes <= static_cast<uint32_t>(a.slot_nz_bytes);
-            uint8_t* dst = smem + sm.slots + slot * slot_bytes;
-            mbar_expect_tx(&bars[slot], 1024u + ((fits && bytes) ? bytes : 0u));
-            bulk_g2s(dst, (is_v ? v_bmp : k_bmp) + blk * 128, 1024u, &bars[slot]);
-            if (fits && bytes) bulk_g2s(dst + 1024, (is_v ? v_nz : k_nz) + static_cast<uint64_t>(off0) * 4u, bytes, &bars[slot]);
-        }
-    };
-    if (tid == 0) issue_until(kSlots);
-
-    const LaneConst lc = make_lane_const();
-    const uint32_t rec_base = smem_u32(rec) + lc.half * 8u;
-
-    float m_run[G], l_run[G], o_acc[G][2];
+    float o_acc[G][2];
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        m_run[g] = -INFINITY;
-        l_run[g] = 0.f;
-        o_acc[g][0] = o_acc[g][1] = 0.f;
-    }
-    const __half* mask = p.mask ? static_cast<const __half*>(p.mask) + static_cast<int64_t>(b) * p.mask_stride : nullptr;
+    for (int g = 0; g < G; ++g) o_acc[g][0] = o_acc[g][1] = 0.f;
 
-    for (int n = 0; n < nb; ++n) {
-        // =============================== K item ===============================
-        {
-            const int item = 2 * n, slot = item & (kSlots - 1);
-            mbar_wait(&bars[slot], (item / kSlots) & 1);
-            const uint8_t* sl = smem + sm.slots + slot * slot_bytes;
-            const uint32_t seg0 = segk[n * 4], segw = segk[n * 4 + warp];
-            const bool fits = (segk[n * 4 + 4] - seg0) * 4u <= static_cast<uint32_t>(a.slot_nz_bytes);
-            const uint8_t* gblk = k_nz + static_cast<uint64_t>(seg0) * 4u;
-            const uint32_t nz_addr = (fits ? smem_u32(sl + 1024) : 0u) + (segw - seg0) * 4u;
-            __syncwarp();
-            build_records(reinterpret_cast<const uint64_t*>(sl) + warp * 32, nz_addr, rec);
-            __syncwarp();
-            float sc[G][2];
-#pragma unroll
-            for (int g = 0; g < G; ++g) sc[g][0] = sc[g][1] = 0.f;
-            if (fits) {
-#pragma unroll 4
-                for (int j = 0; j < 32; ++j) {
-                    float v0, v1;
-                    decode_pair<true>(rec_base + j * 16, lc, nullptr, v0, v1);
-                    const float* qc = qs + (warp * 32 + j) * G;
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        sc[g][0] = fmaf(qc[g], v0, sc[g][0]);
-                        sc[g][1] = fmaf(qc[g], v1, sc[g][1]);
-                    }
+    if (warp == kWarpProducer) {
+        // =========================== producer ===========================
+        if (lane == 0) {
+            const uint64_t* k_bmp = p.k_bmp + static_cast<int64_t>(unit) * p.bmp_stride + static_cast<int64_t>(blk0) * 128;
+            const uint64_t* v_bmp = p.v_bmp + static_cast<int64_t>(unit) * p.bmp_stride + static_cast<int64_t>(blk0) * 128;
+            int s = 0;
+            uint32_t par = 1;  // fresh barrier: the "previous" phase counts as complete
+            for (int n = 0; n < nb; ++n, ++s) {
+                if (s == D) {
+                    s = 0;
+                    par ^= 1;
                 }
-            } else {
-#pragma unroll 2
-                for (int j = 0; j < 32; ++j) {
-                    float v0, v1;
-                    decode_pair<false>(rec_base + j * 16, lc, gblk, v0, v1);
-                    const float* qc = qs + (warp * 32 + j) * G;
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        sc[g][0] = fmaf(qc[g], v0, sc[g][0]);
-                        sc[g][1] = fmaf(qc[g], v1, sc[g][1]);
-                    }
+                for (int is_v = 0; is_v < 2; ++is_v) {
+                    uint64_t* full = &bars[(is_v ? Bars::kFullV : Bars::kFullK) + s];
+                    mbar_wait(&bars[(is_v ? Bars::kEmptyV : Bars::kEmptyK) + s], par);
+                    const uint32_t* seg = is_v ? segv : segk;
+                    const uint32_t off0 = seg[n * 4], bytes = (seg[n * 4 + 4] - off0) * 4u;
+                    const bool fits = bytes <= static_cast<uint32_t>(a.slot_nz_bytes);
+                    uint8_t* dst = smem + (is_v ? sm.slots_v : sm.slots_k) + s * slot_bytes;
+                    mbar_expect_tx(full, 1024u + ((fits && bytes) ? bytes : 0u));
+                    bulk_g2s(dst, (is_v ? v_bmp : k_bmp) + n * 128, 1024u, full);
+                    if (fits && bytes) bulk_g2s(dst + 1024, (is_v ? v_nz : k_nz) + static_cast<uint64_t>(off0) * 4u, bytes, full);
                 }
             }
-            float* sp = spart + (((n & 1) * kAttnWarps + warp) * G) * 64;
-#pragma unroll
-            for (int g = 0; g < G; ++g) *reinterpret_cast<float2*>(sp + g * 64 + 2 * lane) = make_float2(sc[g][0], sc[g][1]);
         }
-        __syncthreads();  // (A) all warps are done with K(n) and V(n-1)
-        if (tid == 0) issue_until(2 * n + 5);
-
-        // =============================== softmax update ===============================
-        {
-            const float* sp = spart + ((n & 1) * kAttnWarps * G) * 64;
-            const int tok = (blk0 + n) * kBlockTokens + 2 * lane;
+    } else if (warp == kWarpSoftmax) {
+        // =========================== online softmax ===========================
+        const bool ref_round = (p.flags & MFB200_F_REF_SCORE_ROUNDING) != 0;
+        const __half* mask = p.mask ? static_cast<const __half*>(p.mask) + static_cast<int64_t>(b) * p.mask_stride : nullptr;
+        float m_run[G], l_run[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            m_run[g] = -INFINITY;
+            l_run[g] = 0.f;
+        }
+        for (int n = 0; n < nb; ++n) {
+            const int buf = n & 1;
+            const uint32_t par = (n >> 1) & 1;
             float mk0 = 0.f, mk1 = 0.f;
             if (mask) {
+                const int tok = (blk0 + n) * kBlockTokens + 2 * lane;
                 mk0 = __half2float(mask[tok]);
                 mk1 = __half2float(mask[tok + 1]);
             }
+            mbar_wait(&bars[Bars::kScFull + buf], par);
+            float s0[G], s1[G];
+            const float* sp = spart + buf * kTileWarps * G * 64;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                float s0 = 0.f, s1 = 0.f;
+                s0[g] = s1[g] = 0.f;
 #pragma unroll
-                for (int w = 0; w < kAttnWarps; ++w) {
+                for (int w = 0; w < kTileWarps; ++w) {
                     const float2 t = *reinterpret_cast<const float2*>(sp + (w * G + g) * 64 + 2 * lane);
-                    s0 += t.x;
-                    s1 += t.y;
+                    s0[g] += t.x;
+                    s1[g] += t.y;
                 }
-                s0 = ref_round_score(s0, p.score_div, ref_round);
-                s1 = ref_round_score(s1, p.score_div, ref_round);
-                if (mask) {
-                    s0 = fmaxf(s0 + mk0, -65504.f);
-                    s1 = fmaxf(s1 + mk1, -65504.f);
-                }
-                const float bm = warp_max(fmaxf(s0, s1));
-                const float m_new = fmaxf(m_run[g], bm);
-                const float corr = exp2f((m_run[g] - m_new) * kLog2e);  // exp2(-inf) = 0 on the first block
-                const float p0 = exp2f((s0 - m_new) * kLog2e), p1 = exp2f((s1 - m_new) * kLog2e);
-                l_run[g] = l_run[g] * corr + warp_sum(p0 + p1);
-                o_acc[g][0] *= corr;
-                o_acc[g][1] *= corr;
-                m_run[g] = m_new;
-                ps[(2 * lane) * G + g] = p0;
-                ps[(2 * lane + 1) * G + g] = p1;
             }
-        }
-        // =============================== V item ===============================
-        {
-            const int item = 2 * n + 1, slot = item & (kSlots - 1);
-            mbar_wait(&bars[slot], (item / kSlots) & 1);
-            const uint8_t* sl = smem + sm.slots + slot * slot_bytes;
-            const uint32_t seg0 = segv[n * 4], segw = segv[n * 4 + warp];
-            const bool fits = (segv[n * 4 + 4] - seg0) * 4u <= static_cast<uint32_t>(a.slot_nz_bytes);
-            const uint8_t* gblk = v_nz + static_cast<uint64_t>(seg0) * 4u;
-            const uint32_t nz_addr = (fits ? smem_u32(sl + 1024) : 0u) + (segw - seg0) * 4u;
-            __syncwarp();  // ps written, K records no longer read
-            build_records(reinterpret_cast<const uint64_t*>(sl) + warp * 32, nz_addr, rec);
             __syncwarp();
-            // this warp's tiles: channel half (warp>>1), tokens 32*(warp&1) .. +31
-            const float* pw = ps + (32 * (warp & 1)) * G;
-            if (fits) {
-#pragma unroll 4
-                for (int j = 0; j < 32; ++j) {
-                    float v0, v1;
-                    decode_pair<true>(rec_base + j * 16, lc, nullptr, v0, v1);
+            if (lane == 0) mbar_arrive(&bars[Bars::kScEmpty + buf]);
+            float p0[G], p1[G], cr[G];
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const float pj = pw[j * G + g];
-                        o_acc[g][0] = fmaf(pj, v0, o_acc[g][0]);
-                        o_acc[g][1] = fmaf(pj, v1, o_acc[g][1]);
-                    }
+            for (int g = 0; g < G; ++g) {
+                float a0 = ref_round_score(s0[g], p.score_div, ref_round);
+                float a1 = ref_round_score(s1[g], p.score_div, ref_round);
+                if (mask) {
+                    a0 = fmaxf(a0 + mk0, -65504.f);
+                    a1 = fmaxf(a1 + mk1, -65504.f);
                 }
-            } else {
-#pragma unroll 2
-                for (int j = 0; j < 32; ++j) {
-                    float v0, v1;
-                    decode_pair<false>(rec_base + j * 16, lc, gblk, v0, v1);
+                const float m_new = fmaxf(m_run[g], warp_max(fmaxf(a0, a1)));
+                cr[g] = exp2f((m_run[g] - m_new) * kLog2e);  // exp2(-inf) = 0 on the first block
+                p0[g] = exp2f((a0 - m_new) * kLog2e);
+                p1[g] = exp2f((a1 - m_new) * kLog2e);
+                l_run[g] = l_run[g] * cr[g] + warp_sum(p0[g] + p1[g]);
+                m_run[g] = m_new;
+            }
+            mbar_wait(&bars[Bars::kPEmpty + buf], par ^ 1);
+            __half* pb = ps + buf * 64 * G;
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const float pj = pw[j * G + g];
-                        o_acc[g][0] = fmaf(pj, v0, o_acc[g][0]);
-                        o_acc[g][1] = fmaf(pj, v1, o_acc[g][1]);
-                    }
+            for (int g = 0; g < G; ++g) {
+                pb[(2 * lane) * G + g] = __float2half_rn(p0[g]);
+                pb[(2 * lane + 1) * G + g] = __float2half_rn(p1[g]);
+                if (lane == 0) corr[buf * 8 + g] = cr[g];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[Bars::kPFull + buf]);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                stat[g] = m_run[g];
+                stat[8 + g] = l_run[g];
+            }
+        }
+    } else {
+        // =========================== K / V tile warps ===========================
+        const bool is_v = warp >= kWarpV0;
+        const int w = warp & 3;
+        const LaneConst lc = make_lane_const();
+        uint2* rec = reinterpret_cast<uint2*>(smem + sm.rec) + warp * 64;
+        const uint2* my_rec = rec + lc.half;
+        const uint32_t* seg = is_v ? segv : segk;
+        const uint8_t* nz_g = is_v ? v_nz : k_nz;
+        const uint32_t slots_off = is_v ? sm.slots_v : sm.slots_k;
+        const int full0 = is_v ? Bars::kFullV : Bars::kFullK, empty0 = is_v ? Bars::kEmptyV : Bars::kEmptyK;
+        int s = 0;
+        uint32_t par = 0;
+        for (int n = 0; n < nb; ++n, ++s) {
+            if (s == D) {
+                s = 0;
+                par ^= 1;
+            }
+            const int buf = n & 1;
+            const uint32_t par2 = (n >> 1) & 1;
+            const uint8_t* sl = smem + slots_off + s * slot_bytes;
+            const uint32_t sg0 = seg[n * 4];
+            const bool fits = (seg[n * 4 + 4] - sg0) * 4u <= static_cast<uint32_t>(a.slot_nz_bytes);
+            const uint8_t* gblk = nz_g + static_cast<uint64_t>(sg0) * 4u;
+            const uint32_t nz_addr = (fits ? smem_u32(sl + 1024) : 0u) + (seg[n * 4 + w] - sg0) * 4u;
+            mbar_wait(&bars[full0 + s], par);
+            build_records(reinterpret_cast<const uint64_t*>(sl) + w * 32, nz_addr, rec);
+            __syncwarp();
+            if (!is_v) {
+                // K item: tiles = channels 32w .. 32w+31 -> partial scores of tokens (2*lane, 2*lane+1)
+                float sc[G][2];
+#pragma unroll
+                for (int g = 0; g < G; ++g) sc[g][0] = sc[g][1] = 0.f;
+                tiles32<G>(fits, my_rec, lc, gblk, qs + (32 * w) * G, sc);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[empty0 + s]);
+                mbar_wait(&bars[Bars::kScEmpty + buf], par2 ^ 1);
+                float* sp = spart + ((buf * kTileWarps + w) * G) * 64;
+#pragma unroll
+                for (int g = 0; g < G; ++g) *reinterpret_cast<float2*>(sp + g * 64 + 2 * lane) = make_float2(sc[g][0], sc[g][1]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[Bars::kScFull + buf]);
+            } else {
+                // V item: tiles 32w .. 32w+31 = channel half (w>>1), tokens 32*(w&1)+j -> channels (2*lane, 2*lane+1)
+                mbar_wait(&bars[Bars::kPFull + buf], par2);
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float c = corr[buf * 8 + g];
+                    o_acc[g][0] *= c;
+                    o_acc[g][1] *= c;
+                }
+                tiles32<G>(fits, my_rec, lc, gblk, ps + (buf * 64 + 32 * (w & 1)) * G, o_acc);
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&bars[empty0 + s]);
+                    mbar_arrive(&bars[Bars::kPEmpty + buf]);
                 }
             }
         }
     }
-    // ---- cross-warp reduction of o: warps (0,1) hold channel half 0, warps (2,3) half 1 ------------
+    // ---- cross-warp reduction of o: V warps (0,1) hold channel half 0, (2,3) half 1 -------------------
     __syncthreads();
-    float* red = spart;                      // [warps][G][64]
-    float* ored = spart + kAttnWarps * G * 64;  // [G][128]
+    float* red = spart;                                          // [4][G][64]
+    float* ored = reinterpret_cast<float*>(smem + sm.slots_k);   // [G][128] (the rings are idle now)
+    if (warp >= kWarpV0 && warp < kWarpV0 + kTileWarps) {
+        const int w = warp & 3;
 #pragma unroll
-    for (int g = 0; g < G; ++g) *reinterpret_cast<float2*>(red + (warp * G + g) * 64 + 2 * lane) = make_float2(o_acc[g][0], o_acc[g][1]);
-    __syncthreads();
-    {
-        const int hf = tid >> 6, e = tid & 63;
-#pragma unroll
-        for (int g = 0; g < G; ++g) ored[g * 128 + tid] = red[((2 * hf) * G + g) * 64 + e] + red[((2 * hf + 1) * G + g) * 64 + e];
+        for (int g = 0; g < G; ++g) *reinterpret_cast<float2*>(red + (w * G + g) * 64 + 2 * lane) = make_float2(o_acc[g][0], o_acc[g][1]);
     }
     __syncthreads();
-    write_partial_and_merge<G>(a, unit, split, ored, m_run, l_run);
+    for (int i = tid; i < G * 128; i += kAttnThreads) {
+        const int g = i >> 7, c = i & 127, hf = c >> 6, e = c & 63;
+        ored[i] = red[((2 * hf) * G + g) * 64 + e] + red[((2 * hf + 1) * G + g) * 64 + e];
+    }
+    __syncthreads();
+    write_partial_and_merge<G>(a, unit, split, ored, stat, stat + 8);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Dense window split: <= 256 tokens of the fp16 residual window (models/llama_mustafar_kernel.py:278, :316).
+// Dense window split: <= 64 tokens of the fp16 residual window (models/llama_mustafar_kernel.py:278, :316).
+// The chunk's K rows and V rows are contiguous (64 x 256 B each): one elected thread fetches both with
+// two bulk copies at kernel entry, so the whole split costs a single DRAM round trip; scores, softmax
+// and P.V then run out of shared memory.  Uses the first 8 warps of the CTA.
+struct WinSmem {
+    uint32_t kw, vw, bar, qs, sw, red, ored, ml, total;
+};
+__host__ __device__ inline WinSmem win_smem_map(int G) {
+    WinSmem m;
+    uint32_t o = 0;
+    m.kw = o;
+    o += kWinTokensPerSplit * kHeadDim * 2;
+    m.vw = o;
+    o += kWinTokensPerSplit * kHeadDim * 2;
+    m.bar = o;
+    o += 16;
+    m.qs = o;  // float [128][G]
+    o += kHeadDim * G * 4;
+    m.sw = o;  // float [G][64] scores, then probabilities
+    o += G * kWinTokensPerSplit * 4;
+    m.red = o;  // float [8 warps][G][128]
+    o += kWinWarps * G * 128 * 4;
+    m.ored = o;  // float [G][128]
+    o += G * 128 * 4;
+    m.ml = o;  // float m[8], l[8]
+    o += 64;
+    m.total = o;
+    return m;
+}
+
 template <int G>
 __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem, int unit, int split) {
     const mfb200_decode_params& p = a.p;
+    const WinSmem sm = win_smem_map(G);
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t lane = lane_id();
-    const int wsplit = split - a.n_csplit;
-    const int t0 = wsplit * kWinTokensPerSplit;
+    const bool active = warp < kWinWarps;
+    const int t0 = (split - a.n_csplit) * kWinTokensPerSplit;
     const int nt = min(kWinTokensPerSplit, p.win_len - t0);
-    const int b = unit / p.kv_heads, h = unit % p.kv_heads;
+    const int b = unit / p.kv_heads;
     const bool ref_round = (p.flags & MFB200_F_REF_SCORE_ROUNDING) != 0;
 
-    float* qs = reinterpret_cast<float*>(smem);               // [c][G]
-    float* sw = qs + kHeadDim * G;                            // [G][256] scores, then probabilities
-    float* red = sw + G * kWinTokensPerSplit;                 // [warps][G][128]
-    float* ored = red + kAttnWarps * G * 128;                 // [G][128]
-    float* stat = ored + G * 128;                             // [warps][G] scratch for block max / sum
+    const __half* kw_s = reinterpret_cast<const __half*>(smem + sm.kw);
+    const __half* vw_s = reinterpret_cast<const __half*>(smem + sm.vw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + sm.bar);
+    float* qs = reinterpret_cast<float*>(smem + sm.qs);
+    float* sw = reinterpret_cast<float*>(smem + sm.sw);
+    float* red = reinterpret_cast<float*>(smem + sm.red);
+    float* ored = reinterpret_cast<float*>(smem + sm.ored);
+    float* ml = reinterpret_cast<float*>(smem + sm.ml);
 
-    {
-        const __half* q = static_cast<const __half*>(p.q) + (static_cast<int64_t>(b) * p.kv_heads + h) * G * kHeadDim;
-#pragma unroll
-        for (int g = 0; g < G; ++g) qs[tid * G + g] = __half2float(q[g * kHeadDim + tid]);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        const __half* kw = static_cast<const __half*>(p.k_win) + static_cast<int64_t>(unit) * p.win_stride + static_cast<int64_t>(t0) * kHeadDim;
+        const __half* vw = static_cast<const __half*>(p.v_win) + static_cast<int64_t>(unit) * p.win_stride + static_cast<int64_t>(t0) * kHeadDim;
+        const uint32_t bytes = static_cast<uint32_t>(nt) * kHeadDim * 2;
+        mbar_expect_tx(bar, 2 * bytes);
+        bulk_g2s(smem + sm.kw, kw, bytes, bar);
+        bulk_g2s(smem + sm.vw, vw, bytes, bar);
     }
-    __syncthreads();
-    const __half* kw = static_cast<const __half*>(p.k_win) + static_cast<int64_t>(unit) * p.win_stride + static_cast<int64_t>(t0) * kHeadDim;
-    const __half* vw = static_cast<const __half*>(p.v_win) + static_cast<int64_t>(unit) * p.win_stride + static_cast<int64_t>(t0) * kHeadDim;
-
-    // ---- scores: 8 lanes per token, lane reads two 16-byte chunks (channels 8s..8s+7, 64+8s..64+8s+7)
     {
+        const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
+        for (int i = tid; i < G * kHeadDim; i += kAttnThreads) qs[(i & 127) * G + (i >> 7)] = __half2float(q[i]);
+    }
+    __syncthreads();  // q staged, barrier initialised
+    mbar_wait(bar, 0);
+    // fused append: the step's new K/V row belongs at window row win_len-1; the split that owns that row
+    // takes it from k_new/v_new (the bulk copy fetched a stale row there) and stores it to the window.
+    if (p.k_new != nullptr && p.win_len - 1 >= t0 && p.win_len - 1 < t0 + nt) {
+        if (tid < 32) {
+            const int r = p.win_len - 1 - t0;
+            const bool is_v = tid >= 16;
+            const int j = tid & 15;
+            const uint4 row = reinterpret_cast<const uint4*>(is_v ? p.v_new : p.k_new)[static_cast<int64_t>(unit) * 16 + j];
+            reinterpret_cast<uint4*>(smem + (is_v ? sm.vw : sm.kw))[r * 16 + j] = row;
+            uint4* gw = reinterpret_cast<uint4*>(static_cast<__half*>(is_v ? p.v_win : p.k_win) +
+                                                 static_cast<int64_t>(unit) * p.win_stride + static_cast<int64_t>(p.win_len - 1) * kHeadDim);
+            gw[j] = row;
+        }
+        __syncthreads();
+    }
+
+    // ---- scores: 8 lanes per token, lane reads two 16-byte chunks (channels 8s..8s+7, 64+8s..64+8s+7);
+    //      a quarter-warp reads 128 contiguous bytes -> conflict-free.  Warp w: tokens 8w..8w+7.
+    if (active) {
         const int tsub = lane >> 3, seg = lane & 7;
         float qr[G][16];
 #pragma unroll
@@ -378,116 +535,80 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
                 qr[g][i] = qs[(8 * seg + i) * G + g];
                 qr[g][8 + i] = qs[(64 + 8 * seg + i) * G + g];
             }
-        constexpr int kUnroll = 4;
-        for (int it = 0; it * 16 * kUnroll < nt; ++it) {
-            uint4 ka[kUnroll], kb[kUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int t = (it * kUnroll + u) * 16 + warp * 4 + tsub;
-                if (t < nt) {
-                    ka[u] = ldg_stream_v4(kw + static_cast<int64_t>(t) * kHeadDim + 8 * seg);
-                    kb[u] = ldg_stream_v4(kw + static_cast<int64_t>(t) * kHeadDim + 64 + 8 * seg);
-                } else {
-                    ka[u] = make_uint4(0, 0, 0, 0);
-                    kb[u] = make_uint4(0, 0, 0, 0);
-                }
+        for (int u = 0; u < 2; ++u) {
+            const int t = warp * 8 + u * 4 + tsub;
+            const uint4 ka = *reinterpret_cast<const uint4*>(kw_s + t * kHeadDim + 8 * seg);
+            const uint4 kb = *reinterpret_cast<const uint4*>(kw_s + t * kHeadDim + 64 + 8 * seg);
+            const uint32_t w[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+            float acc[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) acc[g] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+#pragma unroll
+                for (int g = 0; g < G; ++g) acc[g] = fmaf(qr[g][2 * i + 1], f.y, fmaf(qr[g][2 * i], f.x, acc[g]));
             }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int t = (it * kUnroll + u) * 16 + warp * 4 + tsub;
-                const uint32_t w[8] = {ka[u].x, ka[u].y, ka[u].z, ka[u].w, kb[u].x, kb[u].y, kb[u].z, kb[u].w};
-                float acc[G];
-#pragma unroll
-                for (int g = 0; g < G; ++g) acc[g] = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-#pragma unroll
-                    for (int g = 0; g < G; ++g) acc[g] = fmaf(qr[g][2 * i + 1], f.y, fmaf(qr[g][2 * i], f.x, acc[g]));
-                }
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    float s = acc[g];
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    s += __shfl_xor_sync(0xffffffffu, s, 4);
-                    if (seg == 0 && t < nt) sw[g * kWinTokensPerSplit + t] = s;
-                }
+            for (int g = 0; g < G; ++g) {
+                float s = acc[g];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                if (seg == 0) sw[g * kWinTokensPerSplit + t] = s;  // rows >= nt hold stale smem: masked below
             }
         }
     }
     __syncthreads();
-    // ---- softmax over the nt window tokens (thread owns tokens tid and tid+128) -----------------------
-    float m_loc[G], l_loc[G];
-    {
+    // ---- softmax over the nt tokens: warp g handles head g (lane owns tokens lane, lane+32) ---------------
+    if (warp < G) {
+        const int g = warp;
         const __half* mask = p.mask ? static_cast<const __half*>(p.mask) + static_cast<int64_t>(b) * p.mask_stride + p.comp_len + t0 : nullptr;
+        float s[2];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            float s[2];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int t = tid + r * 128;
-                s[r] = -INFINITY;
-                if (t < nt) {
-                    s[r] = ref_round_score(sw[g * kWinTokensPerSplit + t], p.score_div, ref_round);
-                    if (mask) s[r] = fmaxf(s[r] + __half2float(mask[t]), -65504.f);
-                }
+        for (int r = 0; r < 2; ++r) {
+            const int t = lane + 32 * r;
+            s[r] = -INFINITY;
+            if (t < nt) {
+                s[r] = ref_round_score(sw[g * kWinTokensPerSplit + t], p.score_div, ref_round);
+                if (mask) s[r] = fmaxf(s[r] + __half2float(mask[t]), -65504.f);
             }
-            const float wm = warp_max(fmaxf(s[0], s[1]));
-            if (lane == 0) stat[warp * G + g] = wm;
-            __syncthreads();
-            float mx = stat[g];
+        }
+        const float mx = warp_max(fmaxf(s[0], s[1]));
+        float e[2];
 #pragma unroll
-            for (int w = 1; w < kAttnWarps; ++w) mx = fmaxf(mx, stat[w * G + g]);
-            __syncthreads();
-            float ls = 0.f;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int t = tid + r * 128;
-                if (t < nt) {
-                    const float e = exp2f((s[r] - mx) * kLog2e);
-                    sw[g * kWinTokensPerSplit + t] = e;
-                    ls += e;
-                }
-            }
-            ls = warp_sum(ls);
-            if (lane == 0) stat[warp * G + g] = ls;
-            __syncthreads();
-            float tot = 0.f;
-#pragma unroll
-            for (int w = 0; w < kAttnWarps; ++w) tot += stat[w * G + g];
-            __syncthreads();
-            m_loc[g] = mx;
-            l_loc[g] = tot;
+        for (int r = 0; r < 2; ++r) {
+            const int t = lane + 32 * r;
+            e[r] = (t < nt) ? exp2f((s[r] - mx) * kLog2e) : 0.f;
+            sw[g * kWinTokensPerSplit + t] = e[r];
+        }
+        const float tot = warp_sum(e[0] + e[1]);
+        if (lane == 0) {
+            ml[g] = mx;
+            ml[8 + g] = tot;
         }
     }
-    // ---- P.V: warp takes tokens == warp (mod 4); lane owns channels 4*lane .. 4*lane+3 -----------------
-    {
+    __syncthreads();
+    // ---- P.V: warp w takes tokens 8w..8w+7; lane owns channels 4*lane .. 4*lane+3 ---------------------------
+    if (active) {
         float o[G][4];
 #pragma unroll
         for (int g = 0; g < G; ++g) o[g][0] = o[g][1] = o[g][2] = o[g][3] = 0.f;
-        constexpr int kUnroll = 8;
-        for (int it = 0; it * 4 * kUnroll < nt; ++it) {
-            uint2 vv[kUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int t = (it * kUnroll + u) * 4 + warp;
-                vv[u] = (t < nt) ? ldg_stream_v2(vw + static_cast<int64_t>(t) * kHeadDim + 4 * lane) : make_uint2(0, 0);
-            }
+        for (int u = 0; u < 8; ++u) {
+            const int t = warp * 8 + u;
+            if (t < nt) {
+                const uint2 vv = *reinterpret_cast<const uint2*>(vw_s + t * kHeadDim + 4 * lane);
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&vv.x));
+                const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&vv.y));
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int t = (it * kUnroll + u) * 4 + warp;
-                if (t < nt) {
-                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&vv[u].x));
-                    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&vv[u].y));
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const float pt = sw[g * kWinTokensPerSplit + t];
-                        o[g][0] = fmaf(pt, f0.x, o[g][0]);
-                        o[g][1] = fmaf(pt, f0.y, o[g][1]);
-                        o[g][2] = fmaf(pt, f1.x, o[g][2]);
-                        o[g][3] = fmaf(pt, f1.y, o[g][3]);
-                    }
+                for (int g = 0; g < G; ++g) {
+                    const float pt = sw[g * kWinTokensPerSplit + t];
+                    o[g][0] = fmaf(pt, f0.x, o[g][0]);
+                    o[g][1] = fmaf(pt, f0.y, o[g][1]);
+                    o[g][2] = fmaf(pt, f1.x, o[g][2]);
+                    o[g][3] = fmaf(pt, f1.y, o[g][3]);
                 }
             }
         }
@@ -495,28 +616,28 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
         for (int g = 0; g < G; ++g) *reinterpret_cast<float4*>(red + (warp * G + g) * 128 + 4 * lane) = make_float4(o[g][0], o[g][1], o[g][2], o[g][3]);
     }
     __syncthreads();
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
+    for (int i = tid; i < G * 128; i += kAttnThreads) {
+        const int g = i >> 7, c = i & 127;
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < kAttnWarps; ++w) s += red[(w * G + g) * 128 + tid];
-        ored[g * 128 + tid] = s;
+        for (int w = 0; w < kWinWarps; ++w) s += red[(w * G + g) * 128 + c];
+        ored[i] = s;
     }
     __syncthreads();
-    write_partial_and_merge<G>(a, unit, split, ored, m_loc, l_loc);
+    write_partial_and_merge<G>(a, unit, split, ored, ml, ml + 8);
 }
 
 template <int G>
-__global__ void __launch_bounds__(kAttnThreads) sparse_decode_attn_kernel(const __grid_constant__ DecodeArgs a) {
+__global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 ? 2 : 1))) sparse_decode_attn_kernel(const __grid_constant__ DecodeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int unit = blockIdx.y, split = blockIdx.x;
-    if (split < a.n_csplit) compressed_split<G>(a, smem, unit, split);
-    else window_split<G>(a, smem, unit, split);
+    // 1-D grid, long CTAs first: all compressed splits of all units, then the short window splits.
+    const int units = a.p.batch * a.p.kv_heads;
+    const int id = blockIdx.x, n_comp = a.n_csplit * units;
+    if (id < n_comp) compressed_split<G>(a, smem, id % units, id / units);
+    else window_split<G>(a, smem, (id - n_comp) % units, a.n_csplit + (id - n_comp) / units);
 }
 
-static size_t window_smem_bytes(int G) {
-    return static_cast<size_t>(kHeadDim * G + G * kWinTokensPerSplit + kAttnWarps * G * 128 + G * 128 + kAttnWarps * G) * 4;
-}
+static size_t window_smem_bytes(int G) { return win_smem_map(G).total; }
 
 static int pick_slot_nz_bytes(const mfb200_decode_params* p) {
     // capacity of one ring slot's nonzero area; without a hint the worst case (every element kept).
@@ -525,9 +646,11 @@ static int pick_slot_nz_bytes(const mfb200_decode_params* p) {
     return kb * 1024;
 }
 
+static int pick_depth(int slot_nz_bytes) { return slot_nz_bytes <= 8 * 1024 ? 3 : 2; }
+
 template <int G>
 static int launch_decode(const DecodeArgs& a, cudaStream_t s) {
-    const SmemMap sm = smem_map(G, a.slot_nz_bytes);
+    const SmemMap sm = smem_map(G, a.slot_nz_bytes, a.depth);
     size_t smem = a.n_csplit > 0 ? sm.total : 0;
     if (a.n_wsplit > 0) smem = smem > window_smem_bytes(G) ? smem : window_smem_bytes(G);
     static size_t configured = 0;
@@ -536,15 +659,9 @@ static int launch_decode(const DecodeArgs& a, cudaStream_t s) {
                                       static_cast<int>(smem)));
         configured = smem;
     }
-    dim3 grid(a.n_csplit + a.n_wsplit, a.p.batch * a.p.kv_heads);
+    dim3 grid((a.n_csplit + a.n_wsplit) * a.p.batch * a.p.kv_heads);
     sparse_decode_attn_kernel<G><<<grid, kAttnThreads, smem, s>>>(a);
     return launch_status("sparse_decode_attn_kernel");
-}
-
-static void split_counts(int comp_len, int win_len, int n_split, int* n_csplit, int* n_wsplit) {
-    const int nw = (win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit;
-    *n_wsplit = nw;
-    *n_csplit = n_split - nw;
 }
 
 }  // namespace mfb
@@ -563,13 +680,18 @@ extern "C" int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_
         MFB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     const int64_t units = static_cast<int64_t>(batch) * kv_heads;
-    MFB_REQUIRE(units <= 65535, "decode_plan: batch*kv_heads=%lld exceeds 65535", static_cast<long long>(units));
+    MFB_REQUIRE(units <= (1 << 20), "decode_plan: batch*kv_heads=%lld exceeds 2^20", static_cast<long long>(units));
     const int nblk = comp_len / kBlockTokens;
     const int nw = (win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit;
     int nc = 0;
     if (nblk > 0) {
-        const int64_t target_ctas = static_cast<int64_t>(sm_count) * 3;  // ~3 resident CTAs per SM
-        int64_t per_unit = (target_ctas + units - 1) / units - nw;
+        // Every CTA of the launch should be resident at once (a second, nearly empty wave doubles the
+        // time of a batch-1 launch): splits per unit = floor(resident CTA slots / units) - window CTAs.
+        // Window CTAs are short (one DRAM round trip) and are dispatched last: reserve a quarter slot each.
+        const int64_t slots = static_cast<int64_t>(sm_count) * (groups <= 1 ? MFB_G1_CTAS : (groups <= 4 ? 2 : 1));
+        int64_t reserve = (units * nw + 3) / 4;
+        if (reserve > slots / 8) reserve = slots / 8;
+        int64_t per_unit = (slots - reserve) / units;
         const int min_c = (nblk + kMaxBlocksPerSplit - 1) / kMaxBlocksPerSplit;
         if (per_unit < min_c) per_unit = min_c;
         if (per_unit > nblk) per_unit = nblk;
@@ -585,7 +707,7 @@ extern "C" int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_
 extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb200_stream_t stream) {
     MFB_REQUIRE(p != nullptr, "decode: null params");
     MFB_REQUIRE(p->batch > 0 && p->kv_heads > 0, "decode: batch/kv_heads must be positive");
-    MFB_REQUIRE(static_cast<int64_t>(p->batch) * p->kv_heads <= 65535, "decode: too many units");
+    MFB_REQUIRE(static_cast<int64_t>(p->batch) * p->kv_heads <= (1 << 20), "decode: too many units");
     MFB_REQUIRE(p->groups == 1 || p->groups == 2 || p->groups == 4 || p->groups == 8, "decode: groups=%d not in {1,2,4,8}", p->groups);
     MFB_REQUIRE(p->comp_len >= 0 && p->comp_len % 64 == 0, "decode: comp_len=%d must be a multiple of 64", p->comp_len);
     MFB_REQUIRE(p->win_len >= 0 && p->comp_len + p->win_len >= 1, "decode: empty context");
@@ -607,14 +729,19 @@ extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb
                     "decode: window buffers must be 16-byte aligned");
     }
     if (p->mask) MFB_REQUIRE(p->mask_stride >= p->comp_len + p->win_len, "decode: mask_stride too small");
+    MFB_REQUIRE((p->k_new == nullptr) == (p->v_new == nullptr), "decode: k_new and v_new must be given together");
+    if (p->k_new)
+        MFB_REQUIRE(p->win_len >= 1 && ((reinterpret_cast<uintptr_t>(p->k_new) | reinterpret_cast<uintptr_t>(p->v_new)) & 15) == 0,
+                    "decode: k_new/v_new need win_len >= 1 and 16-byte alignment");
     DecodeArgs a;
     a.p = *p;
-    split_counts(p->comp_len, p->win_len, p->n_split, &a.n_csplit, &a.n_wsplit);
+    a.n_wsplit = (p->win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit;
+    a.n_csplit = p->n_split - a.n_wsplit;
     const int nblk = p->comp_len / kBlockTokens;
-    MFB_REQUIRE(p->n_split >= 1 && a.n_csplit >= (nblk + kMaxBlocksPerSplit - 1) / kMaxBlocksPerSplit && a.n_csplit <= nblk &&
-                    (nblk == 0 || a.n_csplit >= 1),
+    MFB_REQUIRE(p->n_split >= 1 && a.n_csplit >= (nblk + kMaxBlocksPerSplit - 1) / kMaxBlocksPerSplit && a.n_csplit <= nblk,
                 "decode: n_split=%d inconsistent with comp_len=%d win_len=%d (use mfb200_decode_plan)", p->n_split, p->comp_len, p->win_len);
     a.slot_nz_bytes = pick_slot_nz_bytes(p);
+    a.depth = pick_depth(a.slot_nz_bytes);
     auto s = static_cast<cudaStream_t>(stream);
     switch (p->groups) {
         case 1: return launch_decode<1>(a, s);

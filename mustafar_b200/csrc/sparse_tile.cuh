@@ -2,14 +2,20 @@
 //
 // The reference kernels (kernel/csrc/SpMM_Kernel.cuh:109-151) rebuild a dense 256x64 tile in shared
 // memory with a per-thread serial __clzll walk and then run mma.sync over it.  Here nothing is
-// materialised: a warp owns 32 consecutive tiles of a 64-token block; inside a tile every lane owns
-// the two ADJACENT positions (2*lane, 2*lane+1), so the rank of its first position needs ONE popc of
-// the 32-bit half-word that holds it and the second rank is rank+bit0.  Lanes 0-15 work on the high
-// word (positions 0-31), lanes 16-31 on the low word; a per-warp "record" prepared once per tile
-// group stores {word, smem byte address of the word's first nonzero} so the inner loop is
-//     LDS.64 record -> LOP -> POPC -> IMAD -> 2x LDS.U16 -> 2 selects -> FMA(s)
-// per 64 positions.  K tiles (one channel x 64 tokens) give the lane two token scores; V tiles
-// (one token x 64 channels) give it two output channels.
+// materialised: inside a tile every lane owns the two ADJACENT positions (2*lane, 2*lane+1), so the
+// rank of its first position needs ONE popc of the 32-bit half-word that holds it and the second
+// rank is rank+bit0.  Lanes 0-15 work on the high word (positions 0-31), lanes 16-31 on the low
+// word; a "record" prepared once per tile stores {word, smem byte address of the word's first
+// nonzero} so the inner loop is, per 64 positions,
+//     LDS.64 record, LOP3 (mask), POPC, IMAD (address), 2x LDS.U16, 2x LOP3->predicate, SEL,
+//     2x @p FHFMA
+// FHFMA is Blackwell's mixed-precision FMA (PTX fma.rn.f32.f16: fp16 x fp16 + fp32 -> fp32, one
+// rounding): the fp16 nonzero and the fp16 operand (q or p) are multiplied without any conversion
+// instruction and accumulated in fp32.
+//
+// Measured on B200 (tools/ubench.cu): POPC/FLO/BREV issue at 0.5 warp-instr/clk/SM, integer ALU
+// (LOP3/IADD3/SHF/SEL) at 2, IMAD ~2, FFMA 4, LDS ~1 — shared-memory wavefronts (3 per tile here) and
+// issue slots are what bound the loop, so both are kept minimal.
 #pragma once
 #include "common.cuh"
 
@@ -17,7 +23,8 @@ namespace mfb {
 
 struct LaneConst {
     uint32_t above;  // mask of the bits (positions) before this lane's pair inside its 32-bit word
-    uint32_t shift;  // left shift that brings the lane's pair to bits 31,30
+    uint32_t bit0;   // mask of the lane's first position
+    uint32_t bit1;   // mask of the lane's second position
     uint32_t half;   // 0: high word (positions 0..31), 1: low word
 };
 
@@ -25,15 +32,17 @@ __device__ __forceinline__ LaneConst make_lane_const() {
     LaneConst lc;
     const uint32_t l = lane_id();
     const uint32_t sub = l & 15;
-    lc.shift = 2 * sub;
+    lc.bit0 = 0x80000000u >> (2 * sub);
+    lc.bit1 = 0x40000000u >> (2 * sub);
     lc.above = sub == 0 ? 0u : (0xffffffffu << (32 - 2 * sub));
     lc.half = l >> 4;
     return lc;
 }
 
-// Per-warp record table: rec[tile j in 0..31][half] = {bitmap word, byte address of its first value}.
-// `bmp` points at the 32 bitmaps of this warp's tile group in shared memory, `nz_addr` is the
-// (shared-space byte address | byte offset from a global base) of the group's first nonzero.
+// Record table of one 32-tile group: rec[2*j + half] = {bitmap word, byte address of its first value}.
+// Executed by one full warp (lane j <-> tile j).  `bmp` points at the group's 32 bitmaps in shared
+// memory, `nz_addr` is the (shared-space byte address | byte offset from a global base) of the
+// group's first nonzero.
 __device__ __forceinline__ void build_records(const uint64_t* bmp, uint32_t nz_addr, uint2* rec) {
     const uint32_t l = lane_id();
     const uint64_t bm = bmp[l];
@@ -51,30 +60,53 @@ __device__ __forceinline__ void build_records(const uint64_t* bmp, uint32_t nz_a
     rec[2 * l + 1] = make_uint2(lo, start + 2u * pc_hi);
 }
 
-// Values (as fp16 bit patterns, 0 when the bit is clear) of this lane's two positions in tile j.
+// acc + a*b with a, b fp16 (bit patterns) and fp32 accumulation: SASS FHFMA.
+__device__ __forceinline__ float fhfma(uint16_t a, uint16_t b, float acc) {
+    asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(a), "h"(b));
+    return acc;
+}
+
+// fp16 bit patterns of this lane's two positions in one tile: x is valid iff b0, y iff b1 (otherwise
+// they hold whatever the load returned and must not be used -> callers predicate their FMAs).
+struct DecodedPair {
+    uint16_t x, y;
+    bool b0, b1;
+};
+
 template <bool NZ_SHARED>
-__device__ __forceinline__ void decode_pair(uint32_t rec_addr, const LaneConst& lc, const uint8_t* gbase,
-                                            float& v0, float& v1) {
-    const uint2 r = lds_v2(rec_addr);
+__device__ __forceinline__ DecodedPair decode_pair(const uint2* rec, const LaneConst& lc, const uint8_t* gbase) {
+    const uint2 r = *rec;
     const uint32_t w = r.x;
-    const uint32_t addr = r.y + 2u * __popc(w & lc.above);
-    const uint32_t sh = w << lc.shift;
-    const bool b0 = (sh & 0x80000000u) != 0, b1 = (sh & 0x40000000u) != 0;
+    uint32_t addr;  // r.y + 2*rank as one IMAD: keeps the half-rate integer-ALU pipe free
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(__popc(w & lc.above)), "r"(r.y));
+    DecodedPair d;
+    d.b0 = (w & lc.bit0) != 0;
+    d.b1 = (w & lc.bit1) != 0;
     uint32_t x, y;
     if (NZ_SHARED) {
-        // unconditional: a clear bit reads the next value / padding / stale bytes inside our own
-        // shared allocation and is discarded by the selects below.
+        // x unconditional: with a clear bit it reads the next value / padding / stale bytes inside our
+        // own shared allocation and is never used.  The second value sits one slot further iff b0.
         x = lds_u16(addr);
-        y = lds_u16(addr + 2);
+        y = lds_u16(addr + 2);  // unconditional too: keeps the predicates' live ranges short (see callers)
     } else {
         // overflow path (block larger than the staging slot): values come straight from global,
         // predicated so that nothing is read past the end of the buffer.
         const uint16_t* g = reinterpret_cast<const uint16_t*>(gbase + addr);
-        x = (b0 || b1) ? g[0] : 0;
-        y = (b0 && b1) ? g[1] : 0;
+        x = (d.b0 || d.b1) ? g[0] : 0;
+        y = (d.b0 && d.b1) ? g[1] : 0;
     }
-    v0 = b0 ? h2f_bits(x) : 0.f;
-    v1 = b1 ? h2f_bits(b0 ? y : x) : 0.f;
+    d.x = static_cast<uint16_t>(x);
+    d.y = static_cast<uint16_t>(d.b0 ? y : x);  // the pair's second value sits one slot further iff b0
+    return d;
+}
+
+// Same, converted to fp32 with cleared positions forced to 0 (reference-compatible SpMV kernels).
+template <bool NZ_SHARED>
+__device__ __forceinline__ void decode_pair(const uint2* rec, const LaneConst& lc, const uint8_t* gbase, float& v0,
+                                            float& v1) {
+    const DecodedPair d = decode_pair<NZ_SHARED>(rec, lc, gbase);
+    v0 = d.b0 ? h2f_bits(d.x) : 0.f;
+    v1 = d.b1 ? h2f_bits(d.y) : 0.f;
 }
 
 }  // namespace mfb

@@ -67,7 +67,7 @@ key_formulation_kernel(const uint64_t* __restrict__ bmp, const uint8_t* __restri
     const LaneConst lc = make_lane_const();
     build_records(s.bmp + warp * 32, smem_u32(s.nz) + (s.seg[warp] - s.seg[0]) * 4u, s.rec[warp]);
     __syncwarp();
-    const uint32_t rec_base = smem_u32(s.rec[warp]) + lc.half * 8u;
+    const uint2* rec_base = s.rec[warp] + lc.half;
     float sc[8][2];
 #pragma unroll
     for (int n = 0; n < 8; ++n) sc[n][0] = sc[n][1] = 0.f;
@@ -75,7 +75,7 @@ key_formulation_kernel(const uint64_t* __restrict__ bmp, const uint8_t* __restri
 #pragma unroll 4
         for (int j = 0; j < 32; ++j) {
             float v0, v1;
-            decode_pair<true>(rec_base + j * 16, lc, nullptr, v0, v1);
+            decode_pair<true>(rec_base + 2 * j, lc, nullptr, v0, v1);
             const float q = s.vec[(warp * 32 + j) * 8];
             sc[0][0] = fmaf(q, v0, sc[0][0]);
             sc[0][1] = fmaf(q, v1, sc[0][1]);
@@ -84,7 +84,7 @@ key_formulation_kernel(const uint64_t* __restrict__ bmp, const uint8_t* __restri
 #pragma unroll 2
         for (int j = 0; j < 32; ++j) {
             float v0, v1;
-            decode_pair<true>(rec_base + j * 16, lc, nullptr, v0, v1);
+            decode_pair<true>(rec_base + 2 * j, lc, nullptr, v0, v1);
             const float* q = s.vec + (warp * 32 + j) * 8;
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
@@ -126,7 +126,7 @@ value_formulation_kernel(const uint64_t* __restrict__ bmp, const uint8_t* __rest
     const uint8_t* nz_h = nz + static_cast<uint64_t>(nz_offset[h]) * 16u;
     const __half* bp = B + static_cast<int64_t>(bq) * 8 * L;
     const LaneConst lc = make_lane_const();
-    const uint32_t rec_base = smem_u32(s.rec[warp]) + lc.half * 8u;
+    const uint2* rec_base = s.rec[warp] + lc.half;
     float o[8][2];
 #pragma unroll
     for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = 0.f;
@@ -149,7 +149,7 @@ value_formulation_kernel(const uint64_t* __restrict__ bmp, const uint8_t* __rest
 #pragma unroll 4
             for (int j = 0; j < 32; ++j) {
                 float v0, v1;
-                decode_pair<true>(rec_base + j * 16, lc, nullptr, v0, v1);
+                decode_pair<true>(rec_base + 2 * j, lc, nullptr, v0, v1);
                 const float pj = pw[j * 8];
                 o[0][0] = fmaf(pj, v0, o[0][0]);
                 o[0][1] = fmaf(pj, v1, o[0][1]);
@@ -158,7 +158,7 @@ value_formulation_kernel(const uint64_t* __restrict__ bmp, const uint8_t* __rest
 #pragma unroll 2
             for (int j = 0; j < 32; ++j) {
                 float v0, v1;
-                decode_pair<true>(rec_base + j * 16, lc, nullptr, v0, v1);
+                decode_pair<true>(rec_base + 2 * j, lc, nullptr, v0, v1);
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
                     const float pj = pw[j * 8 + n];

@@ -34,7 +34,7 @@ def test_struct_layout_matches_header():
     from mustafar_b200 import _lib
     # 10 x int32/float, then 8-byte fields only
     assert _lib.DecodeParams.q.offset == 40
-    assert C.sizeof(_lib.DecodeParams) == 40 + 18 * 8
+    assert C.sizeof(_lib.DecodeParams) == 40 + 20 * 8
 
 
 def test_argument_validation_without_gpu(lib):

@@ -64,7 +64,64 @@ void run(const char* name, int extra_ops) {
     cudaFree(out);
 }
 
+// ---- shared-memory load shapes: how many wavefronts does a broadcast-ish wide load cost? ----
+template <int MODE>
+__global__ void lds_shape(uint32_t* out, uint32_t seed) {
+    __shared__ __align__(16) uint32_t sm[4096];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = i * 2654435761u + seed;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t acc = 0, off = (threadIdx.x >> 5) * 64;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t base = (off + i * 8 + (it & 7) * 4) & 2047;  // word index, multiple of 4
+            if (MODE == 0) acc += sm[base];                                                   // LDS.32, 1 address
+            if (MODE == 1) acc += sm[base + (lane >> 4)];                                     // LDS.32, 2 addresses
+            if (MODE == 2) { uint2 v = *reinterpret_cast<uint2*>(&sm[base]); acc += v.x ^ v.y; }                 // LDS.64, 1 address
+            if (MODE == 3) { uint2 v = *reinterpret_cast<uint2*>(&sm[base + 2 * (lane >> 4)]); acc += v.x ^ v.y; }  // LDS.64, 2 addresses
+            if (MODE == 4) { uint4 v = *reinterpret_cast<uint4*>(&sm[base]); acc += v.x ^ v.y ^ v.z ^ v.w; }     // LDS.128, 1 address
+            if (MODE == 5) { uint4 v = *reinterpret_cast<uint4*>(&sm[base + 4 * (lane >> 4)]); acc += v.x ^ v.y ^ v.z ^ v.w; }  // LDS.128, 2 addr
+            if (MODE == 6) acc += reinterpret_cast<uint16_t*>(sm)[2 * base + lane + (lane >> 2)];  // LDS.U16, ~40 consecutive halves
+            if (MODE == 7) acc += sm[base + lane];                                                // LDS.32, 32 consecutive words
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+template <int MODE>
+void run_lds(const char* name) {
+    int sms, clk;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    uint32_t* out;
+    const int threads = 512, blocks = sms * 4;
+    cudaMalloc(&out, sizeof(uint32_t) * threads * blocks);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    lds_shape<MODE><<<blocks, threads>>>(out, 1);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    lds_shape<MODE><<<blocks, threads>>>(out, 1);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double n = (double)blocks * (threads / 32) * ITERS * 8;
+    printf("%-28s %8.3f ms  %6.2f clk per warp-load per SM\n", name, ms, ms * 1e-3 * clk * 1e3 * sms / n);
+    cudaFree(out);
+}
+
 int main() {
+    run_lds<0>("LDS.32 1 addr");
+    run_lds<1>("LDS.32 2 addr");
+    run_lds<2>("LDS.64 1 addr");
+    run_lds<3>("LDS.64 2 addr (half-warps)");
+    run_lds<4>("LDS.128 1 addr");
+    run_lds<5>("LDS.128 2 addr (half-warps)");
+    run_lds<6>("LDS.U16 ~40 consecutive");
+    run_lds<7>("LDS.32 32 consecutive");
     run<0>("popc+iadd", 1);
     run<1>("flo(clz)+iadd", 1);
     run<2>("brev+iadd", 1);
