@@ -157,6 +157,14 @@ typedef struct mfb200_decode_params {
 /* Round q·k to fp16 and divide by score_div in fp16 like the reference glue does
  * (SpMM_Kernel.cuh:418, llama_mustafar_kernel.py:284). Off = keep fp32 scores. */
 #define MFB200_F_REF_SCORE_ROUNDING 1
+/* Launch with programmatic stream serialization (PDL): the kernel lets its successor in the stream begin
+ * launching early and itself waits (griddepcontrol.wait) for its predecessors before it touches q, k_new,
+ * v_new, the window or the workspace.  Always safe. */
+#define MFB200_F_PDL 2
+/* With MFB200_F_PDL: additionally request idx / bitmaps / nonzeros of the first blocks BEFORE that wait.
+ * Only valid when the kernel immediately preceding this launch in the stream does not write this cache's
+ * compressed streams (i.e. it is not this cache's own compress_scan/compress_pack). */
+#define MFB200_F_PDL_EARLY_KV 4
 
 /* Chooses the number of sequence splits for a launch and reports the workspace size.
  * sm_count <= 0 → query the current device. Returns n_split (>= 1) or a negative error.

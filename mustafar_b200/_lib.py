@@ -15,6 +15,8 @@ ABI_VERSION = 1
 LAYOUT_KEY = 0
 LAYOUT_VALUE = 1
 F_REF_SCORE_ROUNDING = 1
+F_PDL = 2
+F_PDL_EARLY_KV = 4
 
 _vp = C.c_void_p
 _i64 = C.c_int64

@@ -54,13 +54,16 @@ class MustafarKVCache:
 
     def __init__(self, batch: int, kv_heads: int, groups: int, max_tokens: int, k_sparsity: float, v_sparsity: float,
                  residual_length: int = 32, device="cuda", nz_halves_per_token: Optional[int] = None,
-                 ref_score_rounding: bool = True):
+                 ref_score_rounding: bool = True, pdl: bool = True):
         self.batch, self.kv_heads, self.groups = batch, kv_heads, groups
         self.units = batch * kv_heads
         self.k_sparsity, self.v_sparsity = k_sparsity, v_sparsity
         self.residual_length = residual_length
         self.device = torch.device(device)
         self.ref_score_rounding = ref_score_rounding
+        # programmatic dependent launch: overlap a launch's prologue/first fetches with its predecessor's tail
+        self.pdl = pdl
+        self._streams_dirty = True  # the last launch on this cache rewrote idx/bitmaps/nonzeros
         cap = ((max_tokens + COMPRESS_CHUNK - 1) // COMPRESS_CHUNK) * COMPRESS_CHUNK
         self.cap_tokens = cap
         self.win_cap = residual_length + COMPRESS_CHUNK + 1 if residual_length + COMPRESS_CHUNK < max_tokens else max_tokens + 1
@@ -102,6 +105,7 @@ class MustafarKVCache:
     # ------------------------------------------------------------------ compression
     def _compress_rows(self, stream: _Stream, x: torch.Tensor, layout: int, sparsity: float):
         """Prune + compress x [units, M, 128] and append it at token offset self.comp_len."""
+        self._streams_dirty = True
         units, m, _ = x.shape
         tile_off = self.comp_len * 2
         if m * 2 > self._tmp_bmp.shape[1]:
@@ -191,7 +195,6 @@ class MustafarKVCache:
         """The fields of the C struct that never change for this cache (pointers of the slabs, strides)."""
         p = _lib.DecodeParams()
         p.batch, p.kv_heads, p.groups = self.batch, self.kv_heads, self.groups
-        p.flags = _lib.F_REF_SCORE_ROUNDING if self.ref_score_rounding else 0
         p.score_div = math.sqrt(HEAD_DIM)
         p.slot_kb = self.slot_kb
         p.k_bmp, p.k_idx, p.k_nz, p.k_nz_off = self.k.bmp.data_ptr(), self.k.idx.data_ptr(), self.k.nz.data_ptr(), self.k.nz_off.data_ptr()
@@ -215,6 +218,12 @@ class MustafarKVCache:
             self._ws_bytes = self._ws.numel()
             p.workspace = self._ws.data_ptr()
         p.comp_len, p.win_len, p.n_split = self.comp_len, self.win_len, n_split
+        flags = _lib.F_REF_SCORE_ROUNDING if self.ref_score_rounding else 0
+        if self.pdl:
+            # early KV fetch only if this cache's compressed streams were not just rewritten
+            flags |= _lib.F_PDL if self._streams_dirty else (_lib.F_PDL | _lib.F_PDL_EARLY_KV)
+        self._streams_dirty = False
+        p.flags = flags
         p.q, p.out = q.data_ptr(), out.data_ptr()
         if k_new is not None:
             p.k_new, p.v_new = k_new.data_ptr(), v_new.data_ptr()

@@ -53,10 +53,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-    // not volatile: the address always derives from a record loaded after the relevant barrier, so the
-    // data dependence orders it; leaving it schedulable lets ptxas interleave several tiles.
+    // volatile + memory clobber: the load must stay BEFORE the mbarrier arrive that hands the ring slot
+    // back to the producer.  (A plain asm is a pure function of `addr` to the compiler, which may sink it
+    // — together with the FMA chain it feeds — below the arrive; the slot is then refilled by the next
+    // bulk copy before the load executes.  Seen as sporadic NaNs in one query head of the G=4 build.)
     uint16_t v;
-    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ uint2 lds_v2(uint32_t addr) {

@@ -99,6 +99,11 @@ __host__ __device__ inline SmemMap smem_map(int G, int slot_nz_bytes, int depth)
     return m;
 }
 
+// Programmatic dependent launch (PDL): let the next kernel in the stream start launching, and wait for
+// everything the previous kernels wrote.  Both are no-ops when the kernel was launched normally.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -233,10 +238,15 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     uint32_t* segv = reinterpret_cast<uint32_t*>(smem + sm.segv);
     const uint32_t slot_bytes = 1024u + a.slot_nz_bytes;
 
-    // ---- prologue: q -> fp32 smem, 32-tile segment offsets of this split, barriers ---------------
+    // ---- prologue ------------------------------------------------------------------------------------
+    // With MFB200_F_PDL_EARLY_KV the compressed cache (idx, bitmaps, nonzeros) is known not to be written
+    // by the kernel that precedes this one in the stream, so the segment offsets and the first ring-full of
+    // blocks are requested BEFORE waiting for that kernel: this launch's fetch latency overlaps the
+    // previous launch's tail.  q / k_new / window / workspace are only touched after the wait.
+    const bool early_kv = (p.flags & MFB200_F_PDL_EARLY_KV) != 0;
+    pdl_launch_dependents();
+    if (!early_kv) pdl_wait_prior_grids();
     {
-        const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
-        for (int i = tid; i < G * kHeadDim; i += kAttnThreads) qs[(i & 127) * G + (i >> 7)] = q[i];
         const uint32_t* ki = p.k_idx + static_cast<int64_t>(unit) * p.idx_stride + static_cast<int64_t>(blk0) * 128;
         const uint32_t* vi = p.v_idx + static_cast<int64_t>(unit) * p.idx_stride + static_cast<int64_t>(blk0) * 128;
         for (int i = tid; i <= nb * 4; i += kAttnThreads) {
@@ -260,39 +270,48 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         }
     }
     __syncthreads();
-
     const uint8_t* k_nz = static_cast<const uint8_t*>(p.k_nz) + p.k_nz_off[unit] * 16;
     const uint8_t* v_nz = static_cast<const uint8_t*>(p.v_nz) + p.v_nz_off[unit] * 16;
+    const uint64_t* k_bmp = p.k_bmp + static_cast<int64_t>(unit) * p.bmp_stride + static_cast<int64_t>(blk0) * 128;
+    const uint64_t* v_bmp = p.v_bmp + static_cast<int64_t>(unit) * p.bmp_stride + static_cast<int64_t>(blk0) * 128;
+    // producer state: block n -> ring slot ps_slot, parity ps_par of the slot's EMPTY barrier
+    int pn = 0, ps_slot = 0;
+    uint32_t ps_par = 1;  // fresh barrier: the "previous" phase counts as complete
+    auto produce_until = [&](int limit) {  // producer lane only
+        for (; pn < limit; ++pn, ++ps_slot) {
+            if (ps_slot == D) {
+                ps_slot = 0;
+                ps_par ^= 1;
+            }
+#pragma unroll
+            for (int is_v = 0; is_v < 2; ++is_v) {
+                uint64_t* full = &bars[(is_v ? Bars::kFullV : Bars::kFullK) + ps_slot];
+                mbar_wait(&bars[(is_v ? Bars::kEmptyV : Bars::kEmptyK) + ps_slot], ps_par);
+                const uint32_t* seg = is_v ? segv : segk;
+                const uint32_t off0 = seg[pn * 4], bytes = (seg[pn * 4 + 4] - off0) * 4u;
+                const bool fits = bytes <= static_cast<uint32_t>(a.slot_nz_bytes);
+                uint8_t* dst = smem + (is_v ? sm.slots_v : sm.slots_k) + ps_slot * slot_bytes;
+                mbar_expect_tx(full, 1024u + ((fits && bytes) ? bytes : 0u));
+                bulk_g2s(dst, (is_v ? v_bmp : k_bmp) + pn * 128, 1024u, full);
+                if (fits && bytes) bulk_g2s(dst + 1024, (is_v ? v_nz : k_nz) + static_cast<uint64_t>(off0) * 4u, bytes, full);
+            }
+        }
+    };
+    const bool is_producer = (warp == kWarpProducer) && (lane == 0);
+    if (is_producer) produce_until(nb < D ? nb : D);  // first ring-full: never blocks
+    if (early_kv) pdl_wait_prior_grids();
+    {
+        const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
+        for (int i = tid; i < G * kHeadDim; i += kAttnThreads) qs[(i & 127) * G + (i >> 7)] = q[i];
+    }
+    __syncthreads();  // q staged (threads of every warp contribute) before the K warps read it
     float o_acc[G][2];
 #pragma unroll
     for (int g = 0; g < G; ++g) o_acc[g][0] = o_acc[g][1] = 0.f;
 
     if (warp == kWarpProducer) {
         // =========================== producer ===========================
-        if (lane == 0) {
-            const uint64_t* k_bmp = p.k_bmp + static_cast<int64_t>(unit) * p.bmp_stride + static_cast<int64_t>(blk0) * 128;
-            const uint64_t* v_bmp = p.v_bmp + static_cast<int64_t>(unit) * p.bmp_stride + static_cast<int64_t>(blk0) * 128;
-            int s = 0;
-            uint32_t par = 1;  // fresh barrier: the "previous" phase counts as complete
-            for (int n = 0; n < nb; ++n, ++s) {
-                if (s == D) {
-                    s = 0;
-                    par ^= 1;
-                }
-#pragma unroll
-                for (int is_v = 0; is_v < 2; ++is_v) {
-                    uint64_t* full = &bars[(is_v ? Bars::kFullV : Bars::kFullK) + s];
-                    mbar_wait(&bars[(is_v ? Bars::kEmptyV : Bars::kEmptyK) + s], par);
-                    const uint32_t* seg = is_v ? segv : segk;
-                    const uint32_t off0 = seg[n * 4], bytes = (seg[n * 4 + 4] - off0) * 4u;
-                    const bool fits = bytes <= static_cast<uint32_t>(a.slot_nz_bytes);
-                    uint8_t* dst = smem + (is_v ? sm.slots_v : sm.slots_k) + s * slot_bytes;
-                    mbar_expect_tx(full, 1024u + ((fits && bytes) ? bytes : 0u));
-                    bulk_g2s(dst, (is_v ? v_bmp : k_bmp) + n * 128, 1024u, full);
-                    if (fits && bytes) bulk_g2s(dst + 1024, (is_v ? v_nz : k_nz) + static_cast<uint64_t>(off0) * 4u, bytes, full);
-                }
-            }
-        }
+        if (is_producer) produce_until(nb);
     } else if (warp == kWarpSoftmax) {
         // =========================== online softmax ===========================
         const bool ref_round = (p.flags & MFB200_F_REF_SCORE_ROUNDING) != 0;
@@ -491,6 +510,8 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
     float* ored = reinterpret_cast<float*>(smem + sm.ored);
     float* ml = reinterpret_cast<float*>(smem + sm.ml);
 
+    pdl_launch_dependents();
+    pdl_wait_prior_grids();  // the window is written by the previous step's launch
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -631,6 +652,14 @@ template <int G>
 __global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 ? 2 : 1))) sparse_decode_attn_kernel(const __grid_constant__ DecodeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     // 1-D grid, long CTAs first: all compressed splits of all units, then the short window splits.
+#ifdef MFB_POISON
+    {   // debug: poison the whole dynamic shared memory to expose reads of uninitialised data
+        uint32_t total;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(total));
+        for (uint32_t i = threadIdx.x; i < total / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = MFB_POISON;
+        __syncthreads();
+    }
+#endif
     const int units = a.p.batch * a.p.kv_heads;
     const int id = blockIdx.x, n_comp = a.n_csplit * units;
     if (id < n_comp) compressed_split<G>(a, smem, id % units, id / units);
@@ -659,8 +688,17 @@ static int launch_decode(const DecodeArgs& a, cudaStream_t s) {
                                       static_cast<int>(smem)));
         configured = smem;
     }
-    dim3 grid((a.n_csplit + a.n_wsplit) * a.p.batch * a.p.kv_heads);
-    sparse_decode_attn_kernel<G><<<grid, kAttnThreads, smem, s>>>(a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((a.n_csplit + a.n_wsplit) * a.p.batch * a.p.kv_heads);
+    cfg.blockDim = dim3(kAttnThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (a.p.flags & MFB200_F_PDL) ? 1 : 0;
+    MFB_CUDA(cudaLaunchKernelEx(&cfg, sparse_decode_attn_kernel<G>, a));
     return launch_status("sparse_decode_attn_kernel");
 }
 
