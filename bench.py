@@ -143,6 +143,8 @@ def run_reference(args):
 
 
 def run_ours(args):
+    import ctypes as C
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -178,23 +180,31 @@ def run_ours(args):
     torch.cuda.synchronize()
     units = HEADS
 
-    # per-step synthetic inputs: [layers, 3(q,k,v), heads, 128]
-    n_in = total_steps
-    dev_in = torch.randn(n_in, layers, 3, HEADS, HEAD_DIM, device=dev, dtype=torch.float16)
-    host_in = torch.randn(n_in, layers, 3, HEADS, HEAD_DIM, dtype=torch.float16).pin_memory()
+    # per-step synthetic inputs [layers, 3(q,k,v), heads, 128]; NSETS device-resident sets are rotated, and the
+    # per-layer q/k/v/out views are made once (tensor slicing costs the host more than the FFI call itself)
+    NSETS = 8
+    dev_in = torch.randn(NSETS, layers, 3, HEADS, HEAD_DIM, device=dev, dtype=torch.float16)
+    host_in = torch.randn(total_steps, layers, 3, HEADS, HEAD_DIM, dtype=torch.float16).pin_memory()
     dev_out = torch.empty(layers, HEADS, 1, HEAD_DIM, device=dev, dtype=torch.float16)
     host_out = torch.empty(layers, HEADS, 1, HEAD_DIM, dtype=torch.float16).pin_memory()
     stage_in = torch.empty(layers, 3, HEADS, HEAD_DIM, device=dev, dtype=torch.float16)
+
+    def views(x):
+        return [(x[l, 0].view(1, HEADS, 1, HEAD_DIM), x[l, 1].view(1, HEADS, 1, HEAD_DIM), x[l, 2].view(1, HEADS, 1, HEAD_DIM),
+                 dev_out[l:l + 1]) for l in range(layers)]
+
+    dev_views = [views(dev_in[i]) for i in range(NSETS)]
+    stage_views = views(stage_in)
     launches = [0]
 
-    def step_device(x, compress=True):
-        """x: device tensor [layers, 3, heads, 128].  One fused (append + attention) launch per layer."""
-        for l, c in enumerate(caches):
+    def step_device(vw):
+        """vw: per-layer (q, k_new, v_new, out) views.  One fused (append + attention) launch per layer."""
+        for c, (q, kn, vn, o) in zip(caches, vw):
             before = c.comp_len
-            c.decode_step(x[l, 0].view(1, HEADS, 1, HEAD_DIM), x[l, 1], x[l, 2], out=dev_out[l:l + 1])
+            c.decode_step(q, kn, vn, out=o)
             launches[0] += 1  # fused append + attention: sparse_decode_attn_kernel
             if c.comp_len != before:
-                launches[0] += 6  # K and V: compress_count, compress_scan, compress_pack
+                launches[0] += 1  # compress_append_chunk_kernel: prune + compress 256 window rows of K and V
 
     def timed(fn, n):
         if world > 1:
@@ -221,20 +231,23 @@ def run_ours(args):
 
     # ---- (1) device-resident throughput -------------------------------------------------------------------
     for _ in range(W):
-        step_device(dev_in[nxt()])
+        step_device(dev_views[nxt() % NSETS])
     sampler = ClockSampler(local)
     sampler.start()
     launches[0] = 0
     bytes_before = caches[0].compressed_bytes()
-    ms_dev = timed(lambda i: step_device(dev_in[nxt()]), K)
+    ms_dev = timed(lambda i: step_device(dev_views[nxt() % NSETS]), K)
     gpu_launches = launches[0]
     clocks = sampler.stop()
 
     # ---- (2) dominant kernel alone: 32 attends per step at the current state, CUDA events on the launch stream
     algo_bytes = caches[0].compressed_bytes()
-    q_fix = dev_in[0]
-    params = [c.make_params(q_fix[l, 0].contiguous(), dev_out[l:l + 1]) for l, c in enumerate(caches)]
-    import ctypes as C
+    params = []
+    for l, c in enumerate(caches):
+        pp = _lib.DecodeParams()
+        C.memmove(C.byref(pp), C.byref(c.make_params(dev_views[0][l][0], dev_out[l:l + 1])), C.sizeof(pp))
+        pp.flags |= _lib.F_PDL | _lib.F_PDL_EARLY_KV  # consecutive launches belong to different layer caches
+        params.append(pp)
     sp = _lib.stream_ptr()
     attn = lib.mfb200_sparse_decode_attention
 
@@ -251,7 +264,7 @@ def run_ours(args):
     def step_e2e(_):
         i = nxt()
         stage_in.copy_(host_in[i], non_blocking=True)
-        step_device(stage_in)
+        step_device(stage_views)
         host_out.copy_(dev_out, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller needs this step's result before the next token
 

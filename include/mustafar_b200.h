@@ -89,6 +89,19 @@ int mfb200_compress_pack(const void* x, int64_t heads, int64_t tokens, int layou
                          int64_t tile_offset, const int64_t* head_base, void* packed,
                          int64_t head_capacity, int32_t* overflow, mfb200_stream_t stream);
 
+/* ---- a7: decode-time append of one 256-token chunk (models/llama_mustafar_kernel.py:324-398) ------------
+ * For every unit: prune (prune_k > 0) and compress window rows [0, 256) of K and of V, append them to the
+ * unit's bitmap / idx / nonzero slabs at tile_offset (= 2 * tokens already compressed), then move window rows
+ * [256, win_len) to the front.  One launch, no host sync, no temporaries; the caller then adds 256 to its
+ * compressed length and subtracts 256 from its window length.  Layout of the slabs as in
+ * mfb200_decode_params; head_base in halves; head_capacity / overflow as in mfb200_compress_pack. */
+int mfb200_compress_append_chunk(void* k_win, void* v_win, int64_t win_stride, int64_t units, int win_len,
+                                 int prune_k_key, int prune_k_value, int64_t* k_bmp, int32_t* k_idx, void* k_nz,
+                                 const int64_t* k_head_base, int64_t* v_bmp, int32_t* v_idx, void* v_nz,
+                                 const int64_t* v_head_base, int64_t bmp_stride, int64_t idx_stride,
+                                 int64_t tile_offset, int64_t head_capacity, int32_t* overflow,
+                                 mfb200_stream_t stream);
+
 /* ---- a8-a13: the two batched SpMV operators, reference argument order ----------------------------------
  * C[bq, n, m] (fp16 [Batch_Size, 8, M_Global]).  N_Global must be 8, K_Global 128 (key) /
  * M_Global 128 (value), Split_K is ignored (the reference hard-wires 1).  `A` is unused (NULL in the
@@ -172,6 +185,16 @@ typedef struct mfb200_decode_params {
 int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count,
                        size_t* workspace_bytes, size_t* counter_bytes);
 int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb200_stream_t stream);
+
+/* One decode step on a long-lived parameter block (the host keeps one per layer cache): sets q / out /
+ * k_new / v_new, advances p->win_len by one (the new token), re-plans n_split for the new lengths and
+ * launches mfb200_sparse_decode_attention.  p->workspace must hold mfb200_decode_workspace_max() bytes.
+ * Exists so that a per-layer decode step costs the host a single FFI call. */
+int mfb200_decode_step(mfb200_decode_params* p, const void* q, const void* k_new, const void* v_new, void* out,
+                       int sm_count, mfb200_stream_t stream);
+/* Workspace size that is sufficient for every (comp_len <= max_comp_len, win_len <= max_win_len). */
+size_t mfb200_decode_workspace_max(int batch, int kv_heads, int groups, int max_comp_len, int max_win_len,
+                                   int sm_count);
 
 /* ---- window append (new token's k and v rows) ----------------------------------------------------
  * win[u, pos, :] = row[u, :] for K and V; row: fp16 [units, 128]. */

@@ -49,11 +49,15 @@ SIGNATURES = {
     "mfb200_compress_count": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     "mfb200_compress_scan": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp]),
     "mfb200_compress_pack": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),
+    "mfb200_compress_append_chunk": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                            _i64, _i64, _i64, _i64, _vp, _vp]),
     "mfb200_key_formulation": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32]),
     "mfb200_value_formulation": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32]),
     "mfb200_value_workspace_bytes": (C.c_size_t, [_i32, _i32]),
     "mfb200_decode_plan": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mfb200_sparse_decode_attention": (_i32, [C.POINTER(DecodeParams), _vp]),
+    "mfb200_decode_step": (_i32, [C.POINTER(DecodeParams), _vp, _vp, _vp, _vp, _i32, _vp]),
+    "mfb200_decode_workspace_max": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "mfb200_window_append": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
 }
 

@@ -89,6 +89,9 @@ class MustafarKVCache:
         self._ws_bytes = 0
         self._plan_cache = {}
         self._p = None
+        self._p_ref = None
+        self._p_stale = True
+        self._step = None
         self._sm_count = 0
         self._attn = _lib.load().mfb200_sparse_decode_attention
         # staging capacity for one 64-token block of nonzeros: kept + pad + slack for ties, in KB
@@ -139,6 +142,7 @@ class MustafarKVCache:
             self.k_win[:, :lw].copy_(key_states[:, :, L:].reshape(self.units, lw, d))
             self.v_win[:, :lw].copy_(value_states[:, :, L:].reshape(self.units, lw, d))
             self.win_len = lw
+        self._p_stale = True
 
     def append(self, key_states: torch.Tensor, value_states: torch.Tensor):
         """Append the new token's k/v rows [B, Hkv, 1, 128] to the dense window (`:270`, `:309`)."""
@@ -154,20 +158,26 @@ class MustafarKVCache:
                                             k.data_ptr(), v.data_ptr(), self.units, self.win_len, _lib.stream_ptr()),
                    "mfb200_window_append")
         self.win_len += 1
+        self._p_stale = True
 
     def maybe_compress(self) -> bool:
         """`if (kv_seq_len - residual_length - compressed_length) % 256 == 0` — llama_mustafar_kernel.py:324-398."""
         if self.win_len - self.residual_length != COMPRESS_CHUNK:
             return False
         assert self.comp_len + COMPRESS_CHUNK <= self.cap_tokens, "cache capacity exceeded"
-        with torch.cuda.device(self.device):
-            self._compress_rows(self.k, self.k_win[:, :COMPRESS_CHUNK].contiguous(), _lib.LAYOUT_KEY, self.k_sparsity)
-            self._compress_rows(self.v, self.v_win[:, :COMPRESS_CHUNK].contiguous(), _lib.LAYOUT_VALUE, self.v_sparsity)
-            rest = self.win_len - COMPRESS_CHUNK
-            self.k_win[:, :rest].copy_(self.k_win[:, COMPRESS_CHUNK: self.win_len].clone())
-            self.v_win[:, :rest].copy_(self.v_win[:, COMPRESS_CHUNK: self.win_len].clone())
+        rest = self.win_len - COMPRESS_CHUNK
+        self._streams_dirty = True
+        k, v = self.k, self.v
+        _lib.check(_lib.load().mfb200_compress_append_chunk(
+            self.k_win.data_ptr(), self.v_win.data_ptr(), self.win_cap * HEAD_DIM, self.units, self.win_len,
+            prune_rank(self.k_sparsity), prune_rank(self.v_sparsity),
+            k.bmp.data_ptr(), k.idx.data_ptr(), k.nz.data_ptr(), k.head_base.data_ptr(),
+            v.bmp.data_ptr(), v.idx.data_ptr(), v.nz.data_ptr(), v.head_base.data_ptr(),
+            k.cap_tiles, k.cap_tiles + 1, self.comp_len * 2, min(k.head_capacity, v.head_capacity), self.overflow.data_ptr(),
+            torch.cuda.current_stream(self.device).cuda_stream), "mfb200_compress_append_chunk")
         self.comp_len += COMPRESS_CHUNK
         self.win_len = rest
+        self._p_stale = True
         return True
 
     def check_overflow(self):
@@ -191,6 +201,22 @@ class MustafarKVCache:
         self._plan_cache[key] = (n_split, ws.value)
         return n_split, ws.value
 
+    def _params(self) -> _lib.DecodeParams:
+        """The long-lived C parameter block of this cache (created on first use, with its workspace)."""
+        if self._p is None:
+            lib = _lib.load()
+            self._sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
+            self._p = self._static_params()
+            nbytes = lib.mfb200_decode_workspace_max(self.batch, self.kv_heads, self.groups, self.cap_tokens,
+                                                     self.win_cap, self._sm_count)
+            with torch.cuda.device(self.device):
+                self._ws = torch.zeros((nbytes,), dtype=torch.uint8, device=self.device)
+            self._ws_bytes = nbytes
+            self._p.workspace = self._ws.data_ptr()
+            self._p_ref = C.byref(self._p)
+            self._step = lib.mfb200_decode_step
+        return self._p
+
     def _static_params(self) -> _lib.DecodeParams:
         """The fields of the C struct that never change for this cache (pointers of the slabs, strides)."""
         p = _lib.DecodeParams()
@@ -207,23 +233,12 @@ class MustafarKVCache:
                     k_new: Optional[torch.Tensor] = None, v_new: Optional[torch.Tensor] = None) -> _lib.DecodeParams:
         """Fills the (cached) C parameter block for one launch at the cache's current lengths.  When k_new/v_new
         are given, self.win_len must already count the new token."""
-        if self._p is None:
-            self._sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
-            self._p = self._static_params()
-        p = self._p
+        p = self._params()
         n_split, ws_bytes = self._plan()
-        if self._ws_bytes < ws_bytes:
-            with torch.cuda.device(self.device):
-                self._ws = torch.zeros((max(ws_bytes, 1 << 20),), dtype=torch.uint8, device=self.device)
-            self._ws_bytes = self._ws.numel()
-            p.workspace = self._ws.data_ptr()
+        assert ws_bytes <= self._ws_bytes
         p.comp_len, p.win_len, p.n_split = self.comp_len, self.win_len, n_split
-        flags = _lib.F_REF_SCORE_ROUNDING if self.ref_score_rounding else 0
-        if self.pdl:
-            # early KV fetch only if this cache's compressed streams were not just rewritten
-            flags |= _lib.F_PDL if self._streams_dirty else (_lib.F_PDL | _lib.F_PDL_EARLY_KV)
-        self._streams_dirty = False
-        p.flags = flags
+        self._p_stale = True  # the next fast-path step re-syncs lengths and clears the mask fields
+        p.flags = self._flags()
         p.q, p.out = q.data_ptr(), out.data_ptr()
         if k_new is not None:
             p.k_new, p.v_new = k_new.data_ptr(), v_new.data_ptr()
@@ -234,6 +249,14 @@ class MustafarKVCache:
         else:
             p.mask, p.mask_stride = None, 0
         return p
+
+    def _flags(self) -> int:
+        flags = _lib.F_REF_SCORE_ROUNDING if self.ref_score_rounding else 0
+        if self.pdl:
+            # early KV fetch only if this cache's compressed streams were not just rewritten
+            flags |= _lib.F_PDL if self._streams_dirty else (_lib.F_PDL | _lib.F_PDL_EARLY_KV)
+        self._streams_dirty = False
+        return flags
 
     def _check_q(self, query_states):
         if not query_states.is_cuda or query_states.dtype != torch.float16:
@@ -270,16 +293,33 @@ class MustafarKVCache:
     def decode_step(self, query_states, key_states, value_states, attention_mask=None, out=None):
         """One reference decode step of the attention block (llama_mustafar_kernel.py:256-398) in ONE launch:
         the new token's K/V rows [B, Hkv, 1, 128] are appended to the window by the attention kernel itself,
-        which attends over compressed + window (incl. the new token); then the periodic compression."""
-        assert self.win_len < self.win_cap
-        q = self._check_q(query_states)
-        k = key_states if key_states.is_contiguous() else key_states.contiguous()
-        v = value_states if value_states.is_contiguous() else value_states.contiguous()
-        assert k.numel() == self.units * HEAD_DIM and v.numel() == k.numel() and k.dtype == torch.float16
+        which attends over compressed + window (incl. the new token); then the periodic compression.
+        The unmasked case is a single FFI call (mfb200_decode_step) on the cache's long-lived parameter block."""
+        q, k, v = query_states, key_states, value_states
+        if not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
+            q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        if q.dtype != torch.float16 or not q.is_cuda or k.dtype != torch.float16 or v.dtype != torch.float16:
+            raise RuntimeError("sparse_decode_attention: q/k/v must be float16 CUDA tensors (no CPU fallback)")
+        if (q.numel() != self.units * self.groups * HEAD_DIM or k.numel() != self.units * HEAD_DIM
+                or v.numel() != k.numel() or self.win_len >= self.win_cap):
+            raise ValueError("decode_step: q [B,Hq,1,128], k/v [B,Hkv,1,128] expected and window capacity not exceeded")
         if out is None:
             out = torch.empty_like(q)
-        self.win_len += 1
-        self._launch(self.make_params(q, out, self._mask2d(attention_mask), k, v))
+        if attention_mask is None:
+            p = self._p or self._params()
+            if self._p_stale:  # lengths changed behind the block's back (prefill / compression / masked launch)
+                p.comp_len, p.win_len, p.mask, p.mask_stride = self.comp_len, self.win_len, None, 0
+                self._p_stale = False
+            if self._streams_dirty or not (p.flags & _lib.F_PDL_EARLY_KV):
+                p.flags = self._flags()
+            rc = self._step(self._p_ref, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), self._sm_count,
+                            torch.cuda.current_stream(self.device).cuda_stream)
+            if rc < 0:
+                _lib.check(rc, "mfb200_decode_step")
+            self.win_len += 1
+        else:
+            self.win_len += 1
+            self._launch(self.make_params(q, out, self._mask2d(attention_mask), k, v))
         self.maybe_compress()
         return out
 

@@ -788,3 +788,32 @@ extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb
         default: return launch_decode<8>(a, s);
     }
 }
+
+extern "C" size_t mfb200_decode_workspace_max(int batch, int kv_heads, int groups, int max_comp_len, int max_win_len,
+                                              int sm_count) {
+    size_t best = 0;
+    // n_split is not monotone in the lengths (the window reserve eats into the compressed splits): scan the few
+    // window-chunk counts at the largest compressed length, and the largest window at every chunk boundary.
+    for (int lw = 0; lw <= max_win_len; lw += kWinTokensPerSplit) {
+        size_t ws = 0;
+        const int w = lw == 0 ? (max_comp_len > 0 ? 0 : 1) : lw;
+        if (mfb200_decode_plan(batch, kv_heads, groups, max_comp_len - max_comp_len % 64, w, sm_count, &ws, nullptr) > 0 && ws > best) best = ws;
+    }
+    size_t ws = 0;
+    if (mfb200_decode_plan(batch, kv_heads, groups, max_comp_len - max_comp_len % 64, max_win_len > 0 ? max_win_len : 1, sm_count, &ws, nullptr) > 0 && ws > best) best = ws;
+    return best + 4096;
+}
+
+extern "C" int mfb200_decode_step(mfb200_decode_params* p, const void* q, const void* k_new, const void* v_new, void* out,
+                                  int sm_count, mfb200_stream_t stream) {
+    MFB_REQUIRE(p != nullptr && q && k_new && v_new && out, "decode_step: null pointer");
+    p->q = q;
+    p->out = out;
+    p->k_new = k_new;
+    p->v_new = v_new;
+    p->win_len += 1;
+    const int n = mfb200_decode_plan(p->batch, p->kv_heads, p->groups, p->comp_len, p->win_len, sm_count, nullptr, nullptr);
+    if (n < 0) return n;
+    p->n_split = n;
+    return mfb200_sparse_decode_attention(p, stream);
+}

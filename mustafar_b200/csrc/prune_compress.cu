@@ -206,6 +206,144 @@ compress_pack_kernel(const __half* __restrict__ x, int64_t tokens, const int64_t
     }
 }
 
+// ---- decode-time append: prune + compress the first 256 window rows of every unit, K and V, ONE launch -------
+// (models/llama_mustafar_kernel.py:324-398: dh_prune_* + convert_*_batched + the python index/offset surgery
+// + dropping the 256 rows from the window).  One CTA of 1024 threads owns one (unit, K|V): the 64 KB chunk
+// lives in shared memory, 32 warps prune 8 rows each, bitmap / count / in-CTA scan / pack follow without
+// leaving the CTA, results go straight into the cache slabs at the unit's current tile offset, and the
+// CTA finally moves the remaining window rows to the front.  No host sync, no temporaries, no second read.
+constexpr int kChunkTokens = 256;
+constexpr int kChunkTiles = kChunkTokens * 2;  // 512
+constexpr int kChunkThreads = 1024;
+
+struct ChunkArgs {
+    __half* win[2];          // k_win, v_win: [units, win_stride]
+    int64_t win_stride;      // halves
+    int win_len;             // rows currently in the window (>= 256)
+    int prune_k[2];
+    int64_t* bmp[2];         // [units, bmp_stride]
+    int32_t* idx[2];         // [units, idx_stride]
+    __half* nz[2];
+    const int64_t* head_base[2];  // halves
+    int64_t bmp_stride, idx_stride, tile_offset, head_capacity;
+    int32_t* overflow;
+};
+
+template <int LAYOUT>
+__device__ __forceinline__ void compress_chunk_body(const ChunkArgs& a, int which, uint16_t* tile, uint32_t* bm_hi,
+                                                    uint32_t* bm_lo, int32_t* off, uint16_t (*stage)[64]) {
+    const int64_t h = blockIdx.x;
+    const uint32_t lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    __half* win = a.win[which] + h * a.win_stride;
+    // 1. load + prune: warp w owns rows 8w .. 8w+7
+    {
+        const uint2* src = reinterpret_cast<const uint2*>(win);
+        uint2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ldg_stream_v2(src + (warp * 8 + i) * 32 + lane);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[i] = prune4(v[i], a.prune_k[which]);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(tile + (warp * 8 + i) * kPitch + 4 * lane);
+            dst[0] = v[i].x;
+            dst[1] = v[i].y;
+        }
+    }
+    __syncthreads();
+    // 2. bitmaps + counts: warp w owns tiles 16w .. 16w+15 (token block w/8)
+    const int t0 = warp * 16;
+    const uint16_t* blk = tile + (t0 >> 7) * 64 * kPitch;
+    uint32_t my_hi = 0, my_lo = 0;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        uint32_t e0, e1;
+        tile_elems<LAYOUT>(blk, (t0 + i) & 127, lane, e0, e1);
+        const uint32_t hi = __brev(__ballot_sync(0xffffffffu, (e0 & 0x7fffu) != 0));
+        const uint32_t lo = __brev(__ballot_sync(0xffffffffu, (e1 & 0x7fffu) != 0));
+        if (lane == static_cast<uint32_t>(i)) {
+            my_hi = hi;
+            my_lo = lo;
+        }
+    }
+    if (lane < 16) {
+        bm_hi[t0 + lane] = my_hi;
+        bm_lo[t0 + lane] = my_lo;
+        a.bmp[which][h * a.bmp_stride + a.tile_offset + t0 + lane] =
+            static_cast<int64_t>((static_cast<uint64_t>(my_hi) << 32) | my_lo);
+    }
+    __syncthreads();
+    // 3. exclusive scan of the 512 padded counts (warps 0..15, one tile per lane) on top of the unit's running offset
+    __shared__ int32_t warp_tot[16];
+    int32_t incl = 0, cnt = 0;
+    if (warp < 16) {
+        const int t = warp * 32 + lane;
+        cnt = ((__popc(bm_hi[t]) + __popc(bm_lo[t]) + 7) & ~7) >> 1;
+        incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= static_cast<uint32_t>(o)) incl += n;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+    }
+    __syncthreads();
+    if (warp < 16) {
+        int32_t* idx = a.idx[which] + h * a.idx_stride + a.tile_offset;
+        int32_t base = a.tile_offset > 0 ? idx[0] : 0;
+        for (int w = 0; w < warp; ++w) base += warp_tot[w];
+        const int t = warp * 32 + lane;
+        off[t] = base + incl - cnt;
+        idx[t + 1] = base + incl;
+        if (t == 0 && a.tile_offset == 0) idx[0] = 0;
+    }
+    __syncthreads();
+    // 4. pack: one contiguous (<= 128 B) store per tile
+    const uint32_t above = lane == 0 ? 0u : (0xffffffffu << (32 - lane));
+    const uint32_t mybit = 0x80000000u >> lane;
+    uint16_t* out = reinterpret_cast<uint16_t*>(a.nz[which]) + a.head_base[which][h];
+    uint32_t* st32 = reinterpret_cast<uint32_t*>(stage[warp]);
+#pragma unroll 2
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t hi = bm_hi[t0 + i], lo = bm_lo[t0 + i];
+        const int32_t o2 = off[t0 + i];
+        uint32_t e0, e1;
+        tile_elems<LAYOUT>(blk, (t0 + i) & 127, lane, e0, e1);
+        st32[lane] = 0;
+        __syncwarp();
+        const uint32_t pc_hi = __popc(hi);
+        if (hi & mybit) stage[warp][__popc(hi & above)] = static_cast<uint16_t>(e0);
+        if (lo & mybit) stage[warp][pc_hi + __popc(lo & above)] = static_cast<uint16_t>(e1);
+        __syncwarp();
+        const uint32_t n_pad = (pc_hi + __popc(lo) + 7u) & ~7u;
+        if (a.head_capacity > 0 && 2 * static_cast<int64_t>(o2) + n_pad > a.head_capacity) {
+            if (lane == 0 && a.overflow != nullptr) atomicExch(a.overflow, 1);
+        } else if (2 * lane < n_pad) {
+            reinterpret_cast<uint32_t*>(out + 2 * static_cast<int64_t>(o2))[lane] = st32[lane];
+        }
+        __syncwarp();
+    }
+    // 5. drop the 256 compressed rows: move rows [256, win_len) to the front (all reads of rows < 256 are done)
+    const int rest16 = (a.win_len - kChunkTokens) * 16;  // uint4 per remaining rows
+    uint4* w4 = reinterpret_cast<uint4*>(win);
+    for (int i = threadIdx.x; i < rest16; i += kChunkThreads) {
+        const uint4 v = w4[kChunkTokens * 16 + i];
+        w4[i] = v;  // rest <= 256 rows: source and destination ranges never overlap
+    }
+}
+
+__global__ void __launch_bounds__(kChunkThreads) compress_append_chunk_kernel(const ChunkArgs a) {
+    extern __shared__ __align__(16) uint8_t csm[];
+    uint16_t* tile = reinterpret_cast<uint16_t*>(csm);                                  // [256][kPitch]
+    uint32_t* bm_hi = reinterpret_cast<uint32_t*>(csm + kChunkTokens * kPitch * 2);     // [512]
+    uint32_t* bm_lo = bm_hi + kChunkTiles;
+    int32_t* off = reinterpret_cast<int32_t*>(bm_lo + kChunkTiles);                     // [512]
+    uint16_t(*stage)[64] = reinterpret_cast<uint16_t(*)[64]>(off + kChunkTiles);         // [32][64]
+    if (blockIdx.y == 0) compress_chunk_body<MFB200_LAYOUT_KEY>(a, 0, tile, bm_hi, bm_lo, off, stage);
+    else compress_chunk_body<MFB200_LAYOUT_VALUE>(a, 1, tile, bm_hi, bm_lo, off, stage);
+}
+constexpr size_t kChunkSmem = kChunkTokens * kPitch * 2 + 3 * kChunkTiles * 4 + 32 * 64 * 2;
+
 // ---- window append: win[u, pos, :] = row[u, :] (K and V in one launch) -------------------------
 __global__ void __launch_bounds__(256)
 window_append_kernel(uint4* __restrict__ k_win, uint4* __restrict__ v_win, int64_t win_stride_v4,
@@ -301,4 +439,51 @@ extern "C" int mfb200_window_append(void* k_win, void* v_win, int64_t win_stride
         static_cast<uint4*>(k_win), static_cast<uint4*>(v_win), win_stride / 8, static_cast<const uint4*>(k_row),
         static_cast<const uint4*>(v_row), units, pos);
     return launch_status("window_append_kernel");
+}
+
+extern "C" int mfb200_compress_append_chunk(void* k_win, void* v_win, int64_t win_stride, int64_t units, int win_len,
+                                            int prune_k_key, int prune_k_value, int64_t* k_bmp, int32_t* k_idx, void* k_nz,
+                                            const int64_t* k_head_base, int64_t* v_bmp, int32_t* v_idx, void* v_nz,
+                                            const int64_t* v_head_base, int64_t bmp_stride, int64_t idx_stride,
+                                            int64_t tile_offset, int64_t head_capacity, int32_t* overflow,
+                                            mfb200_stream_t stream) {
+    MFB_REQUIRE(k_win && v_win && k_bmp && k_idx && k_nz && k_head_base && v_bmp && v_idx && v_nz && v_head_base,
+                "compress_append_chunk: null pointer");
+    MFB_REQUIRE(win_len >= kChunkTokens && win_len <= 2 * kChunkTokens, "compress_append_chunk: win_len=%d outside [256, 512]", win_len);
+    MFB_REQUIRE(win_stride >= static_cast<int64_t>(win_len) * kHeadDim && win_stride % 8 == 0, "compress_append_chunk: bad win_stride");
+    MFB_REQUIRE(prune_k_key >= 0 && prune_k_key <= kHeadDim && prune_k_value >= 0 && prune_k_value <= kHeadDim,
+                "compress_append_chunk: prune_k out of [0,128]");
+    MFB_REQUIRE(tile_offset >= 0 && tile_offset % 128 == 0 && bmp_stride >= tile_offset + kChunkTiles && idx_stride >= tile_offset + kChunkTiles + 1,
+                "compress_append_chunk: cache slab too small for tile_offset=%lld", static_cast<long long>(tile_offset));
+    MFB_REQUIRE(units >= 0 && units <= (1 << 20), "compress_append_chunk: units out of range");
+    if (units == 0) return MFB200_OK;
+    static bool configured = false;
+    if (!configured) {
+        MFB_CUDA(cudaFuncSetAttribute(compress_append_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(kChunkSmem)));
+        configured = true;
+    }
+    ChunkArgs a;
+    a.win[0] = static_cast<__half*>(k_win);
+    a.win[1] = static_cast<__half*>(v_win);
+    a.win_stride = win_stride;
+    a.win_len = win_len;
+    a.prune_k[0] = prune_k_key;
+    a.prune_k[1] = prune_k_value;
+    a.bmp[0] = k_bmp;
+    a.bmp[1] = v_bmp;
+    a.idx[0] = k_idx;
+    a.idx[1] = v_idx;
+    a.nz[0] = static_cast<__half*>(k_nz);
+    a.nz[1] = static_cast<__half*>(v_nz);
+    a.head_base[0] = k_head_base;
+    a.head_base[1] = v_head_base;
+    a.bmp_stride = bmp_stride;
+    a.idx_stride = idx_stride;
+    a.tile_offset = tile_offset;
+    a.head_capacity = head_capacity;
+    a.overflow = overflow;
+    dim3 grid(static_cast<unsigned>(units), 2);
+    compress_append_chunk_kernel<<<grid, kChunkThreads, kChunkSmem, static_cast<cudaStream_t>(stream)>>>(a);
+    return launch_status("compress_append_chunk_kernel");
 }
