@@ -286,7 +286,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
 #pragma unroll
             for (int is_v = 0; is_v < 2; ++is_v) {
                 uint64_t* full = &bars[(is_v ? Bars::kFullV : Bars::kFullK) + ps_slot];
-                mbar_wait(&bars[(is_v ? Bars::kEmptyV : Bars::kEmptyK) + ps_slot], ps_par);
+                mbar_wait_relaxed(&bars[(is_v ? Bars::kEmptyV : Bars::kEmptyK) + ps_slot], ps_par);  // producer: sleep between polls
                 const uint32_t* seg = is_v ? segv : segk;
                 const uint32_t off0 = seg[pn * 4], bytes = (seg[pn * 4 + 4] - off0) * 4u;
                 const bool fits = bytes <= static_cast<uint32_t>(a.slot_nz_bytes);
@@ -314,71 +314,66 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         if (is_producer) produce_until(nb);
     } else if (warp == kWarpSoftmax) {
         // =========================== online softmax ===========================
+        // Head-parallel lane mapping: 32/G lanes per query head, each lane owns 2G consecutive tokens of the
+        // block, so all G heads reduce at once with log2(32/G) shuffle steps (the result gates the V warps).
+        constexpr int LPH = 32 / G, TPL = 2 * G;
+        const int hg = lane / LPH, t0 = (lane % LPH) * TPL;
         const bool ref_round = (p.flags & MFB200_F_REF_SCORE_ROUNDING) != 0;
         const __half* mask = p.mask ? static_cast<const __half*>(p.mask) + static_cast<int64_t>(b) * p.mask_stride : nullptr;
-        float m_run[G], l_run[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            m_run[g] = -INFINITY;
-            l_run[g] = 0.f;
-        }
+        float m_run = -INFINITY, l_run = 0.f;
         for (int n = 0; n < nb; ++n) {
             const int buf = n & 1;
             const uint32_t par = (n >> 1) & 1;
-            float mk0 = 0.f, mk1 = 0.f;
-            if (mask) {
-                const int tok = (blk0 + n) * kBlockTokens + 2 * lane;
-                mk0 = __half2float(mask[tok]);
-                mk1 = __half2float(mask[tok + 1]);
-            }
+            float mk[TPL];
+#pragma unroll
+            for (int i = 0; i < TPL; ++i) mk[i] = mask ? __half2float(mask[(blk0 + n) * kBlockTokens + t0 + i]) : 0.f;
             mbar_wait(&bars[Bars::kScFull + buf], par);
-            float s0[G], s1[G];
-            const float* sp = spart + buf * kTileWarps * G * 64;
+            float sc[TPL];
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                s0[g] = s1[g] = 0.f;
+            for (int i = 0; i < TPL; ++i) sc[i] = 0.f;
+            const float* sp = spart + buf * kTileWarps * G * 64 + hg * 64 + t0;
 #pragma unroll
-                for (int w = 0; w < kTileWarps; ++w) {
-                    const float2 t = *reinterpret_cast<const float2*>(sp + (w * G + g) * 64 + 2 * lane);
-                    s0[g] += t.x;
-                    s1[g] += t.y;
+            for (int w = 0; w < kTileWarps; ++w)
+#pragma unroll
+                for (int i = 0; i < TPL; i += 2) {
+                    const float2 t = *reinterpret_cast<const float2*>(sp + w * G * 64 + i);
+                    sc[i] += t.x;
+                    sc[i + 1] += t.y;
                 }
-            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[Bars::kScEmpty + buf]);
-            float p0[G], p1[G], cr[G];
+            float mx = -INFINITY;
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                float a0 = ref_round_score(s0[g], p.score_div, ref_round);
-                float a1 = ref_round_score(s1[g], p.score_div, ref_round);
-                if (mask) {
-                    a0 = fmaxf(a0 + mk0, -65504.f);
-                    a1 = fmaxf(a1 + mk1, -65504.f);
-                }
-                const float m_new = fmaxf(m_run[g], warp_max(fmaxf(a0, a1)));
-                cr[g] = exp2f((m_run[g] - m_new) * kLog2e);  // exp2(-inf) = 0 on the first block
-                p0[g] = exp2f((a0 - m_new) * kLog2e);
-                p1[g] = exp2f((a1 - m_new) * kLog2e);
-                l_run[g] = l_run[g] * cr[g] + warp_sum(p0[g] + p1[g]);
-                m_run[g] = m_new;
+            for (int i = 0; i < TPL; ++i) {
+                sc[i] = ref_round_score(sc[i], p.score_div, ref_round);
+                if (mask) sc[i] = fmaxf(sc[i] + mk[i], -65504.f);
+                mx = fmaxf(mx, sc[i]);
             }
+#pragma unroll
+            for (int o = LPH / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const float m_new = fmaxf(m_run, mx);
+            const float cr = exp2f((m_run - m_new) * kLog2e);  // exp2(-inf) = 0 on the first block
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < TPL; ++i) {
+                sc[i] = exp2f((sc[i] - m_new) * kLog2e);
+                sum += sc[i];
+            }
+#pragma unroll
+            for (int o = LPH / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            l_run = l_run * cr + sum;
+            m_run = m_new;
             mbar_wait(&bars[Bars::kPEmpty + buf], par ^ 1);
-            __half* pb = ps + buf * 64 * G;
+            __half* pb = ps + buf * 64 * G + t0 * G + hg;
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                pb[(2 * lane) * G + g] = __float2half_rn(p0[g]);
-                pb[(2 * lane + 1) * G + g] = __float2half_rn(p1[g]);
-                if (lane == 0) corr[buf * 8 + g] = cr[g];
-            }
+            for (int i = 0; i < TPL; ++i) pb[i * G] = __float2half_rn(sc[i]);
+            if (t0 == 0) corr[buf * 8 + hg] = cr;
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[Bars::kPFull + buf]);
         }
-        if (lane == 0) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                stat[g] = m_run[g];
-                stat[8 + g] = l_run[g];
-            }
+        if (t0 == 0) {
+            stat[hg] = m_run;
+            stat[8 + hg] = l_run;
         }
     } else {
         // =========================== K / V tile warps ===========================
