@@ -23,12 +23,13 @@
 // Every hand-off (slot full/empty, scores full/empty, probabilities full/empty) is an mbarrier, so
 // the K warps run ahead of the V warps by up to two blocks and nobody waits for the slowest warp.
 // Nothing dense is ever rebuilt in shared memory (sparse_tile.cuh).
+#include "gqa_mma.cuh"
 #include "sparse_tile.cuh"
 
 namespace mfb {
 
 #ifndef MFB_G1_CTAS
-#define MFB_G1_CTAS 2  // resident CTAs per SM the G=1 kernel is compiled for
+#define MFB_G1_CTAS 3  // resident CTAs per SM the G=1 kernel is compiled for (64 registers, no spills; +3..6 % at batch 1)
 #endif
 constexpr int kTileWarps = 4;                 // per role
 constexpr int kWarpK0 = 0, kWarpV0 = 4, kWarpSoftmax = 8, kWarpProducer = 9;
@@ -67,7 +68,7 @@ struct Bars {
 };
 
 struct SmemMap {
-    uint32_t slots_k, slots_v, bars, rec, qs, spart, ps, corr, stat, segk, segv, total;
+    uint32_t slots_k, slots_v, bars, rec, qs, spart, ps, corr, stat, segk, segv, dense, total;
 };
 
 __host__ __device__ inline SmemMap smem_map(int G, int slot_nz_bytes, int depth) {
@@ -83,10 +84,10 @@ __host__ __device__ inline SmemMap smem_map(int G, int slot_nz_bytes, int depth)
     o += 2 * kTileWarps * 64 * 8;
     m.qs = o;  // half [128][G]
     o += kHeadDim * G * 2;
-    m.spart = o;  // float [2][4 warps][G][64]; reused for the final cross-warp reduction of o
-    o += 2 * kTileWarps * G * 64 * 4;
-    m.ps = o;  // half [2][64][G]
-    o += 2 * 64 * G * 2;
+    m.spart = o;  // float [2][4 warps][G][sp_pitch]; reused for the final cross-warp reduction of o
+    o += 2 * kTileWarps * G * (G >= 4 ? kTcRowPitch : 64) * 4;
+    m.ps = o;  // half [2][64][G]  (G >= 4: [2][G][kTcRowPitch], token pairs contiguous)
+    o += 2 * (G >= 4 ? kTcRowPitch : 64) * G * 2;
     m.corr = o;  // float [2][8]
     o += 2 * 8 * 4;
     m.stat = o;  // float m[8], l[8]
@@ -95,6 +96,8 @@ __host__ __device__ inline SmemMap smem_map(int G, int slot_nz_bytes, int depth)
     o += (kMaxBlocksPerSplit * 4 + 4) * 4;
     m.segv = o;
     o += (kMaxBlocksPerSplit * 4 + 4) * 4;
+    m.dense = o;  // G >= 4 (tensor-core variant): one 32 x 64 fp16 buffer per tile warp
+    if (G >= 4) o += 2 * kTileWarps * kDenseWarpBytes;
     m.total = o;
     return m;
 }
@@ -308,6 +311,10 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     float o_acc[G][2];
 #pragma unroll
     for (int g = 0; g < G; ++g) o_acc[g][0] = o_acc[g][1] = 0.f;
+    float tc_o[8][2];      // tensor-core variant: V warps' out[g = tc_o_gid][8*nt + 2*tig .. +1]
+    uint32_t tc_o_gid = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tc_o[i][0] = tc_o[i][1] = 0.f;
 
     if (warp == kWarpProducer) {
         // =========================== producer ===========================
@@ -331,12 +338,13 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             float sc[TPL];
 #pragma unroll
             for (int i = 0; i < TPL; ++i) sc[i] = 0.f;
-            const float* sp = spart + buf * kTileWarps * G * 64 + hg * 64 + t0;
+            constexpr int SPP = G >= 4 ? kTcRowPitch : 64;  // row pitch of the partial-score buffer
+            const float* sp = spart + buf * kTileWarps * G * SPP + hg * SPP + t0;
 #pragma unroll
             for (int w = 0; w < kTileWarps; ++w)
 #pragma unroll
                 for (int i = 0; i < TPL; i += 2) {
-                    const float2 t = *reinterpret_cast<const float2*>(sp + w * G * 64 + i);
+                    const float2 t = *reinterpret_cast<const float2*>(sp + w * G * SPP + i);
                     sc[i] += t.x;
                     sc[i + 1] += t.y;
                 }
@@ -364,9 +372,15 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             l_run = l_run * cr + sum;
             m_run = m_new;
             mbar_wait(&bars[Bars::kPEmpty + buf], par ^ 1);
-            __half* pb = ps + buf * 64 * G + t0 * G + hg;
+            if constexpr (G >= 4) {  // tensor-core variant: p as [g][64 tokens] (A-fragment pairs are along tokens)
+                __half* pb = ps + (buf * G + hg) * kTcRowPitch + t0;
 #pragma unroll
-            for (int i = 0; i < TPL; ++i) pb[i * G] = __float2half_rn(sc[i]);
+                for (int i = 0; i < TPL; i += 2) *reinterpret_cast<__half2*>(pb + i) = __floats2half2_rn(sc[i], sc[i + 1]);
+            } else {
+                __half* pb = ps + buf * 64 * G + t0 * G + hg;
+#pragma unroll
+                for (int i = 0; i < TPL; ++i) pb[i * G] = __float2half_rn(sc[i]);
+            }
             if (t0 == 0) corr[buf * 8 + hg] = cr;
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[Bars::kPFull + buf]);
@@ -386,6 +400,22 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         const uint8_t* nz_g = is_v ? v_nz : k_nz;
         const uint32_t slots_off = is_v ? sm.slots_v : sm.slots_k;
         const int full0 = is_v ? Bars::kFullV : Bars::kFullK, empty0 = is_v ? Bars::kEmptyV : Bars::kEmptyK;
+        // tensor-core variant state: q A-fragments (K warps, constant) and the o accumulator fragments (V warps)
+        uint32_t qfrag[2][2] = {{0u, 0u}, {0u, 0u}};
+        float oacc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+        if constexpr (G >= 4) {
+            const uint32_t gid = lane >> 2, tig = lane & 3;
+            if (!is_v && gid < G) {
+                const uint32_t* q32 = reinterpret_cast<const uint32_t*>(static_cast<const __half*>(p.q) +
+                                                                        (static_cast<int64_t>(unit) * G + gid) * kHeadDim + 32 * w);
+                qfrag[0][0] = q32[tig];
+                qfrag[0][1] = q32[4 + tig];
+                qfrag[1][0] = q32[8 + tig];
+                qfrag[1][1] = q32[12 + tig];
+            }
+        }
         int s = 0;
         uint32_t par = 0;
         for (int n = 0; n < nb; ++n, ++s) {
@@ -403,7 +433,52 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             mbar_wait(&bars[full0 + s], par);
             build_records(reinterpret_cast<const uint64_t*>(sl) + w * 32, nz_addr, rec);
             __syncwarp();
-            if (!is_v) {
+            if constexpr (G >= 4) {
+                // ---------- tensor-core variant: decompress to the warp's dense buffer, then 16 HMMA ----------
+                const uint32_t dense_addr = smem_u32(smem + sm.dense) + warp * kDenseWarpBytes;
+                const uint32_t gid = lane >> 2, tig = lane & 3;
+                __syncwarp();  // the previous block's ldmatrix reads of the buffer are done
+                if (fits) decode_to_dense32<true>(my_rec, lc, gblk, dense_addr);
+                else decode_to_dense32<false>(my_rec, lc, gblk, dense_addr);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[empty0 + s]);  // ring slot no longer needed
+                if (!is_v) {
+                    // scores[g][token] += q[g][channels 32w..32w+31] . K : A = q rows (constant), B = dense (channel x token)
+                    float acc[8][4];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+                    mma_dense32(dense_addr, qfrag, acc);
+                    mbar_wait(&bars[Bars::kScEmpty + buf], par2 ^ 1);
+                    if (gid < G) {
+                        float* sp = spart + ((buf * kTileWarps + w) * G + gid) * kTcRowPitch + 2 * tig;
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<float2*>(sp + 8 * nt) = make_float2(acc[nt][0], acc[nt][1]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars[Bars::kScFull + buf]);
+                } else {
+                    // out[g][channel] += p[g][tokens] . V : A = p rows of this block, B = dense (token x channel)
+                    mbar_wait(&bars[Bars::kPFull + buf], par2);
+                    uint32_t pfrag[2][2] = {{0u, 0u}, {0u, 0u}};
+                    float c = 1.f;
+                    if (gid < G) {
+                        const uint32_t pa = smem_u32(ps + (buf * G + gid) * kTcRowPitch + 32 * (w & 1) + 2 * tig);
+                        pfrag[0][0] = lds_u32(pa);
+                        pfrag[0][1] = lds_u32(pa + 16);
+                        pfrag[1][0] = lds_u32(pa + 32);
+                        pfrag[1][1] = lds_u32(pa + 48);
+                        c = corr[buf * 8 + gid];
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars[Bars::kPEmpty + buf]);
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+                        oacc[nt][0] *= c;
+                        oacc[nt][1] *= c;
+                    }
+                    mma_dense32(dense_addr, pfrag, oacc);
+                }
+            } else if (!is_v) {
                 // K item: tiles = channels 32w .. 32w+31 -> partial scores of tokens (2*lane, 2*lane+1)
                 float sc[G][2];
 #pragma unroll
@@ -434,6 +509,19 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                 }
             }
         }
+        if constexpr (G >= 4) {
+            // hand the V warps' accumulator fragments over in the layout the final reduction expects
+            if (is_v) {
+                const uint32_t gid = lane >> 2, tig = lane & 3;
+                tc_o_gid = gid;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    tc_o[nt][0] = oacc[nt][0];
+                    tc_o[nt][1] = oacc[nt][1];
+                }
+                (void)tig;
+            }
+        }
     }
     // ---- cross-warp reduction of o: V warps (0,1) hold channel half 0, (2,3) half 1 -------------------
     __syncthreads();
@@ -441,8 +529,16 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     float* ored = reinterpret_cast<float*>(smem + sm.slots_k);   // [G][128] (the rings are idle now)
     if (warp >= kWarpV0 && warp < kWarpV0 + kTileWarps) {
         const int w = warp & 3;
+        if constexpr (G >= 4) {
+            if (tc_o_gid < G) {
+                float* rp = red + (w * G + tc_o_gid) * 64 + 2 * (lane & 3);
 #pragma unroll
-        for (int g = 0; g < G; ++g) *reinterpret_cast<float2*>(red + (w * G + g) * 64 + 2 * lane) = make_float2(o_acc[g][0], o_acc[g][1]);
+                for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<float2*>(rp + 8 * nt) = make_float2(tc_o[nt][0], tc_o[nt][1]);
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; ++g) *reinterpret_cast<float2*>(red + (w * G + g) * 64 + 2 * lane) = make_float2(o_acc[g][0], o_acc[g][1]);
+        }
     }
     __syncthreads();
     for (int i = tid; i < G * 128; i += kAttnThreads) {
