@@ -127,7 +127,8 @@ typedef struct mfb200_decode_params {
     int32_t win_len;      /* Lw: tokens in the dense window, >= 0; L + Lw >= 1 */
     int32_t flags;        /* MFB200_F_* */
     float score_div;      /* sqrt(head_dim): scores are divided by it (llama_mustafar_kernel.py:284) */
-    int32_t n_split;      /* from mfb200_decode_plan */
+    int32_t n_split;      /* informational (mfb200_decode_plan's return value); the launch derives its own work
+                             decomposition from the geometry, so a stale value is harmless */
     int32_t slot_kb;      /* staging capacity for one 64-token block's nonzeros, KB (1..16); 0 = 16
                              (worst case, every element kept).  Larger blocks still work: they take a
                              slower path that reads their nonzeros straight from global memory. */
@@ -179,15 +180,18 @@ typedef struct mfb200_decode_params {
  * compressed streams (i.e. it is not this cache's own compress_scan/compress_pack). */
 #define MFB200_F_PDL_EARLY_KV 4
 
-/* Chooses the number of sequence splits for a launch and reports the workspace size.
- * sm_count <= 0 → query the current device. Returns n_split (>= 1) or a negative error.
+/* Reports the workspace a launch of this geometry needs.  sm_count <= 0 → query the current device.
+ * Returns the number of partial-result slots per (sequence, KV head) unit (>= 1) or a negative error.
+ * Decomposition (chosen inside the launch, same rule): small launches cut every unit into the same number of
+ * compressed splits so that all CTAs are resident at once; large MHA launches (G <= 2, >= 24 blocks per resident
+ * CTA slot) divide all units*blocks evenly over 1x or 2x the resident CTA slots, CTAs may cross unit boundaries.
  * Workspace layout: [counters: units*4 bytes, rounded to 256][partials fp32]. */
 int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count,
                        size_t* workspace_bytes, size_t* counter_bytes);
 int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb200_stream_t stream);
 
 /* One decode step on a long-lived parameter block (the host keeps one per layer cache): sets q / out /
- * k_new / v_new, advances p->win_len by one (the new token), re-plans n_split for the new lengths and
+ * k_new / v_new, advances p->win_len by one (the new token) and
  * launches mfb200_sparse_decode_attention.  p->workspace must hold mfb200_decode_workspace_max() bytes.
  * Exists so that a per-layer decode step costs the host a single FFI call. */
 int mfb200_decode_step(mfb200_decode_params* p, const void* q, const void* k_new, const void* v_new, void* out,

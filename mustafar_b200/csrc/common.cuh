@@ -89,6 +89,11 @@ __device__ __forceinline__ uint2 ldg_stream_v2(const void* p) {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// Required before the memory of a used mbarrier is initialised again (re-initialising a valid mbarrier is
+// undefined behaviour; it showed up as a hang when one CTA processed two work segments).
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

@@ -23,6 +23,8 @@
 // Every hand-off (slot full/empty, scores full/empty, probabilities full/empty) is an mbarrier, so
 // the K warps run ahead of the V warps by up to two blocks and nobody waits for the slowest warp.
 // Nothing dense is ever rebuilt in shared memory (sparse_tile.cuh).
+#include <stdlib.h>
+
 #include "gqa_mma.cuh"
 #include "sparse_tile.cuh"
 
@@ -46,8 +48,12 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 struct DecodeArgs {
     mfb200_decode_params p;
-    int n_csplit;
-    int n_wsplit;
+    int n_csplit;   // uniform mode: compressed splits per unit
+    int n_wsplit;   // window chunks per unit
+    int flat_ctas;  // flat mode (> 0): number of compressed CTAs n; they partition the B = units*nblk blocks evenly:
+    int flat_q;     //   B / n   -> CTA c owns global blocks [c*q + min(c, r), ...) : q + 1 blocks if c < r, else q
+    int flat_r;     //   B % n
+    int max_split;  // partial slots per unit in the workspace (>= every unit's segment count + n_wsplit)
     int slot_nz_bytes;  // capacity of a slot's nonzero area (multiple of 1024)
     int depth;          // ring depth per stream (K and V each), 2..4
 };
@@ -121,17 +127,33 @@ __device__ __forceinline__ float ref_round_score(float dot, float div, bool ref_
     return dot / div;
 }
 
-// Writes this split's partial (o[G][128] from smem `ored`, m, l) and lets the last CTA of the unit merge.
+// Flat mode: the compressed CTAs partition the launch's units*nblk blocks (unit-major global block index, < 2^31)
+// evenly; a CTA that crosses a unit boundary contributes one segment (= one partial) to each side.
+__host__ __device__ inline uint32_t flat_start(const DecodeArgs& a, uint32_t c) {  // first global block of CTA c
+    return c * a.flat_q + (c < static_cast<uint32_t>(a.flat_r) ? c : a.flat_r);
+}
+__host__ __device__ inline uint32_t flat_owner(const DecodeArgs& a, uint32_t x) {  // CTA that owns global block x
+    const uint32_t big = static_cast<uint32_t>(a.flat_r) * (a.flat_q + 1);         // blocks held by the (q+1)-sized CTAs
+    return x < big ? x / (a.flat_q + 1) : a.flat_r + (x - big) / a.flat_q;
+}
+// number of compressed partials of `unit`
+__host__ __device__ inline int unit_csplits(const DecodeArgs& a, int unit) {
+    if (a.flat_ctas <= 0) return a.n_csplit;
+    const uint32_t nblk = a.p.comp_len / kBlockTokens;
+    return static_cast<int>(flat_owner(a, (unit + 1) * nblk - 1) - flat_owner(a, unit * nblk)) + 1;
+}
+
+// Writes this split's partial (o[G][128] from smem `ored`, m, l) into slot `split` of the unit and lets the last
+// of the unit's `n_split` contributors merge.
 template <int G>
-__device__ __forceinline__ void write_partial_and_merge(const DecodeArgs& a, int unit, int split, const float* ored,
-                                                        const float* m, const float* l) {
+__device__ __forceinline__ void write_partial_and_merge(const DecodeArgs& a, int unit, int split, int n_split,
+                                                        const float* ored, const float* m, const float* l) {
     const mfb200_decode_params& p = a.p;
     const int tid = threadIdx.x;
-    const int n_split = a.n_csplit + a.n_wsplit;
     const int units = p.batch * p.kv_heads;
     int* counters = static_cast<int*>(p.workspace);
     float* parts = reinterpret_cast<float*>(static_cast<uint8_t*>(p.workspace) + ((units * 4 + 255) & ~255));
-    float* mine = parts + (static_cast<int64_t>(unit) * n_split + split) * G * kPartStride;
+    float* mine = parts + (static_cast<int64_t>(unit) * a.max_split + split) * G * kPartStride;
     for (int i = tid; i < G * 128; i += kAttnThreads) mine[(i >> 7) * kPartStride + (i & 127)] = ored[i];
     if (tid < G) {
         mine[tid * kPartStride + 128] = m[tid];
@@ -147,7 +169,7 @@ __device__ __forceinline__ void write_partial_and_merge(const DecodeArgs& a, int
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const float* up = parts + static_cast<int64_t>(unit) * n_split * G * kPartStride;
+    const float* up = parts + static_cast<int64_t>(unit) * a.max_split * G * kPartStride;
     for (int i = tid; i < G * 128; i += kAttnThreads) {
         const int g = i >> 7, c = i & 127;
         float mx = -INFINITY;
@@ -219,15 +241,13 @@ __device__ __forceinline__ void tiles32(bool nz_shared, const uint2* rec, const 
 
 // ------------------------------------------------------------------------------------------------
 template <int G>
-__device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* smem, int unit, int split) {
+__device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* smem, int unit, int split, int n_split,
+                                                 int blk0, int blk1, bool again) {
     const mfb200_decode_params& p = a.p;
     const int D = a.depth;
     const SmemMap sm = smem_map(G, a.slot_nz_bytes, D);
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t lane = lane_id();
-    const int nblk_total = p.comp_len / kBlockTokens;
-    const int blk0 = static_cast<int>(static_cast<int64_t>(split) * nblk_total / a.n_csplit);
-    const int blk1 = static_cast<int>(static_cast<int64_t>(split + 1) * nblk_total / a.n_csplit);
     const int nb = blk1 - blk0;
     const int b = unit / p.kv_heads;
 
@@ -249,6 +269,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     const bool early_kv = (p.flags & MFB200_F_PDL_EARLY_KV) != 0;
     pdl_launch_dependents();
     if (!early_kv) pdl_wait_prior_grids();
+    if (again) __syncthreads();  // flat mode, second segment of this CTA: everyone has left the previous one
     {
         const uint32_t* ki = p.k_idx + static_cast<int64_t>(unit) * p.idx_stride + static_cast<int64_t>(blk0) * 128;
         const uint32_t* vi = p.v_idx + static_cast<int64_t>(unit) * p.idx_stride + static_cast<int64_t>(blk0) * 128;
@@ -257,6 +278,10 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             segv[i] = __ldg(vi + i * 32);
         }
         if (tid == 0) {
+            if (again) {  // re-initialising a live mbarrier is undefined: invalidate the previous segment's first
+#pragma unroll
+                for (int i = 0; i < Bars::kCount; ++i) mbar_inval(&bars[i]);
+            }
             for (int s = 0; s < kMaxDepth; ++s) {
                 mbar_init(&bars[Bars::kFullK + s], 1);
                 mbar_init(&bars[Bars::kEmptyK + s], kTileWarps);
@@ -546,7 +571,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         ored[i] = red[((2 * hf) * G + g) * 64 + e] + red[((2 * hf + 1) * G + g) * 64 + e];
     }
     __syncthreads();
-    write_partial_and_merge<G>(a, unit, split, ored, stat, stat + 8);
+    write_partial_and_merge<G>(a, unit, split, n_split, ored, stat, stat + 8);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -581,13 +606,13 @@ __host__ __device__ inline WinSmem win_smem_map(int G) {
 }
 
 template <int G>
-__device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem, int unit, int split) {
+__device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem, int unit, int split, int n_split, int wchunk) {
     const mfb200_decode_params& p = a.p;
     const WinSmem sm = win_smem_map(G);
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t lane = lane_id();
     const bool active = warp < kWinWarps;
-    const int t0 = (split - a.n_csplit) * kWinTokensPerSplit;
+    const int t0 = wchunk * kWinTokensPerSplit;
     const int nt = min(kWinTokensPerSplit, p.win_len - t0);
     const int b = unit / p.kv_heads;
     const bool ref_round = (p.flags & MFB200_F_REF_SCORE_ROUNDING) != 0;
@@ -736,10 +761,11 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
         ored[i] = s;
     }
     __syncthreads();
-    write_partial_and_merge<G>(a, unit, split, ored, ml, ml + 8);
+    write_partial_and_merge<G>(a, unit, split, n_split, ored, ml, ml + 8);
 }
 
-template <int G>
+// FLAT is a compile-time switch so that the uniform-mode kernel carries no segment-loop state in registers.
+template <int G, bool FLAT>
 __global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 ? 2 : 1))) sparse_decode_attn_kernel(const __grid_constant__ DecodeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     // 1-D grid, long CTAs first: all compressed splits of all units, then the short window splits.
@@ -752,9 +778,37 @@ __global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 
     }
 #endif
     const int units = a.p.batch * a.p.kv_heads;
-    const int id = blockIdx.x, n_comp = a.n_csplit * units;
-    if (id < n_comp) compressed_split<G>(a, smem, id % units, id / units);
-    else window_split<G>(a, smem, (id - n_comp) % units, a.n_csplit + (id - n_comp) / units);
+    const int nblk = a.p.comp_len / kBlockTokens;
+    const int id = blockIdx.x;
+    const int n_comp = FLAT ? a.flat_ctas : a.n_csplit * units;
+    if (id < n_comp) {
+        if constexpr (!FLAT) {  // uniform mode: split `id / units` of unit `id % units`
+            const int unit = id % units, split = id / units;
+            compressed_split<G>(a, smem, unit, split, a.n_csplit + a.n_wsplit, split * nblk / a.n_csplit,
+                                (split + 1) * nblk / a.n_csplit, false);
+        } else {
+            // flat mode: an even cut of all units*nblk blocks, processed as segments cut at unit boundaries (one partial
+            // per segment).  The segment arithmetic is redone per segment from opaque copies of (id, j) so that nothing
+            // but j stays in registers across the split body.
+            for (int j = 0;; ++j) {
+                int idv = id, jv = j;
+                asm volatile("" : "+r"(idv), "+r"(jv));
+                const uint32_t cur = flat_start(a, idv), end = cur + a.flat_q + (idv < a.flat_r ? 1 : 0);
+                const int unit = cur / static_cast<uint32_t>(nblk) + jv;
+                const uint32_t u0 = static_cast<uint32_t>(unit) * nblk;
+                const int b0 = jv == 0 ? cur - u0 : 0;
+                const int b1 = min(static_cast<uint32_t>(nblk), end - u0);
+                const bool more = u0 + nblk < end;
+                compressed_split<G>(a, smem, unit, idv - static_cast<int>(flat_owner(a, u0)), unit_csplits(a, unit) + a.n_wsplit,
+                                    b0, b1, j > 0);
+                if (!more) break;
+            }
+        }
+    } else {  // dense-window chunks come after all compressed CTAs
+        const int unit = (id - n_comp) % units, wchunk = (id - n_comp) / units;
+        const int nc = FLAT ? unit_csplits(a, unit) : a.n_csplit;
+        window_split<G>(a, smem, unit, nc + wchunk, nc + a.n_wsplit, wchunk);
+    }
 }
 
 static size_t window_smem_bytes(int G) { return win_smem_map(G).total; }
@@ -768,19 +822,20 @@ static int pick_slot_nz_bytes(const mfb200_decode_params* p) {
 
 static int pick_depth(int slot_nz_bytes) { return slot_nz_bytes <= 8 * 1024 ? 3 : 2; }
 
-template <int G>
+template <int G, bool FLAT>
 static int launch_decode(const DecodeArgs& a, cudaStream_t s) {
     const SmemMap sm = smem_map(G, a.slot_nz_bytes, a.depth);
-    size_t smem = a.n_csplit > 0 ? sm.total : 0;
+    size_t smem = (a.n_csplit > 0 || a.flat_ctas > 0) ? sm.total : 0;
     if (a.n_wsplit > 0) smem = smem > window_smem_bytes(G) ? smem : window_smem_bytes(G);
     static size_t configured = 0;
     if (smem > configured) {
-        MFB_CUDA(cudaFuncSetAttribute(sparse_decode_attn_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MFB_CUDA(cudaFuncSetAttribute(sparse_decode_attn_kernel<G, FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
         configured = smem;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((a.n_csplit + a.n_wsplit) * a.p.batch * a.p.kv_heads);
+    const int units = a.p.batch * a.p.kv_heads;
+    cfg.gridDim = dim3((a.flat_ctas > 0 ? a.flat_ctas : a.n_csplit * units) + a.n_wsplit * units);
     cfg.blockDim = dim3(kAttnThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
@@ -789,13 +844,77 @@ static int launch_decode(const DecodeArgs& a, cudaStream_t s) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (a.p.flags & MFB200_F_PDL) ? 1 : 0;
-    MFB_CUDA(cudaLaunchKernelEx(&cfg, sparse_decode_attn_kernel<G>, a));
+    MFB_CUDA(cudaLaunchKernelEx(&cfg, sparse_decode_attn_kernel<G, FLAT>, a));
     return launch_status("sparse_decode_attn_kernel");
 }
 
 }  // namespace mfb
 
 using namespace mfb;
+
+namespace mfb {
+struct Plan {
+    int n_csplit, n_wsplit, flat_ctas, flat_q, flat_r, max_split;
+};
+// Work decomposition of one launch.  Every CTA of a small launch should be resident at once (a second, nearly
+// empty wave doubles the time of a batch-1 launch); window CTAs are short and dispatched last, so only a
+// fraction of a slot is reserved for each.
+//  * uniform mode: every unit is cut into the same number of compressed splits;
+//  * flat mode (24..256 blocks per CTA): the launch's units*nblk blocks are divided evenly over exactly the
+//    resident CTA slots, CTAs may cross unit boundaries -> no wave-quantisation loss for mid-size batches.
+static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count) {
+    Plan pl = {0, (win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit, 0, 0, 0, 0};
+    const int64_t units = static_cast<int64_t>(batch) * kv_heads;
+    const int nblk = comp_len / kBlockTokens;
+    if (nblk > 0) {
+        const int64_t slots = static_cast<int64_t>(sm_count) * (groups <= 1 ? MFB_G1_CTAS : (groups <= 4 ? 2 : 1));
+        int64_t reserve = (units * pl.n_wsplit + 3) / 4;
+        if (reserve > slots / 8) reserve = slots / 8;
+        const int64_t avail = slots - reserve;
+        const int64_t B = units * nblk;
+        // testing / tuning override (not API): MFB200_FLAT=0 never uses the flat mode, MFB200_FLAT=n forces n CTAs
+        static const int forced_flat = [] { const char* e = getenv("MFB200_FLAT"); return e ? atoi(e) : -1; }();
+        // flat mode: long CTAs need no reserve for the (short, trailing) window CTAs.  Large MHA launches get two
+        // CTAs per slot (measured: 355 -> 320 us for 128 units x 508 blocks; the hardware scheduler evens out the tail).
+        int64_t n_flat = 0;
+        if (forced_flat > 0) n_flat = forced_flat;
+        else if (forced_flat < 0) {
+            // (G >= 4 launches measured no gain from the flat cut: they are not limited by the tail)
+            if (groups <= 2) n_flat = B / (2 * slots) >= 48 ? 2 * slots : (B / slots >= 24 ? slots : 0);
+        }
+        if (n_flat > B) n_flat = B;
+        if (n_flat > 0 && B < (int64_t{1} << 31) && (B + n_flat - 1) / n_flat <= kMaxBlocksPerSplit) {
+            pl.flat_ctas = static_cast<int>(n_flat);
+            pl.flat_q = static_cast<int>(B / n_flat);
+            pl.flat_r = static_cast<int>(B % n_flat);
+            // a unit's nblk blocks intersect at most ceil(nblk / q) + 1 CTAs
+            pl.max_split = (nblk + pl.flat_q - 1) / pl.flat_q + 1 + pl.n_wsplit;
+            return pl;
+        }
+        int64_t per_unit = avail / units;
+        const int min_c = (nblk + kMaxBlocksPerSplit - 1) / kMaxBlocksPerSplit;
+        if (per_unit < min_c) per_unit = min_c;
+        if (per_unit > nblk) per_unit = nblk;
+        pl.n_csplit = static_cast<int>(per_unit);
+    }
+    pl.max_split = pl.n_csplit + pl.n_wsplit;
+    return pl;
+}
+static int device_sm_count(int* out) {
+    static int cached[64] = {0};
+    int dev = 0;
+    MFB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || cached[dev] == 0) {
+        int n = 0;
+        MFB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < 64) cached[dev] = n;
+        *out = n;
+    } else {
+        *out = cached[dev];
+    }
+    return MFB200_OK;
+}
+}  // namespace mfb
 
 extern "C" int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count,
                                   size_t* workspace_bytes, size_t* counter_bytes) {
@@ -804,33 +923,16 @@ extern "C" int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_
     MFB_REQUIRE(comp_len >= 0 && comp_len % 64 == 0, "decode_plan: comp_len=%d must be a multiple of 64", comp_len);
     MFB_REQUIRE(win_len >= 0 && comp_len + win_len >= 1, "decode_plan: empty context");
     if (sm_count <= 0) {
-        int dev = 0;
-        MFB_CUDA(cudaGetDevice(&dev));
-        MFB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        const int rc = device_sm_count(&sm_count);
+        if (rc) return rc;
     }
     const int64_t units = static_cast<int64_t>(batch) * kv_heads;
     MFB_REQUIRE(units <= (1 << 20), "decode_plan: batch*kv_heads=%lld exceeds 2^20", static_cast<long long>(units));
-    const int nblk = comp_len / kBlockTokens;
-    const int nw = (win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit;
-    int nc = 0;
-    if (nblk > 0) {
-        // Every CTA of the launch should be resident at once (a second, nearly empty wave doubles the
-        // time of a batch-1 launch): splits per unit = floor(resident CTA slots / units) - window CTAs.
-        // Window CTAs are short (one DRAM round trip) and are dispatched last: reserve a quarter slot each.
-        const int64_t slots = static_cast<int64_t>(sm_count) * (groups <= 1 ? MFB_G1_CTAS : (groups <= 4 ? 2 : 1));
-        int64_t reserve = (units * nw + 3) / 4;
-        if (reserve > slots / 8) reserve = slots / 8;
-        int64_t per_unit = (slots - reserve) / units;
-        const int min_c = (nblk + kMaxBlocksPerSplit - 1) / kMaxBlocksPerSplit;
-        if (per_unit < min_c) per_unit = min_c;
-        if (per_unit > nblk) per_unit = nblk;
-        nc = static_cast<int>(per_unit);
-    }
-    const int n_split = nc + nw;
+    const Plan pl = make_plan(batch, kv_heads, groups, comp_len, win_len, sm_count);
     const size_t cbytes = (static_cast<size_t>(units) * 4 + 255) & ~static_cast<size_t>(255);
     if (counter_bytes) *counter_bytes = cbytes;
-    if (workspace_bytes) *workspace_bytes = cbytes + static_cast<size_t>(units) * n_split * groups * kPartStride * 4;
-    return n_split;
+    if (workspace_bytes) *workspace_bytes = cbytes + static_cast<size_t>(units) * pl.max_split * groups * kPartStride * 4;
+    return pl.max_split;  // partial slots per unit (informational; the launch re-derives the plan itself)
 }
 
 extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb200_stream_t stream) {
@@ -864,19 +966,26 @@ extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb
                     "decode: k_new/v_new need win_len >= 1 and 16-byte alignment");
     DecodeArgs a;
     a.p = *p;
-    a.n_wsplit = (p->win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit;
-    a.n_csplit = p->n_split - a.n_wsplit;
-    const int nblk = p->comp_len / kBlockTokens;
-    MFB_REQUIRE(p->n_split >= 1 && a.n_csplit >= (nblk + kMaxBlocksPerSplit - 1) / kMaxBlocksPerSplit && a.n_csplit <= nblk,
-                "decode: n_split=%d inconsistent with comp_len=%d win_len=%d (use mfb200_decode_plan)", p->n_split, p->comp_len, p->win_len);
+    int sm_count = 0;
+    {
+        const int rc = device_sm_count(&sm_count);
+        if (rc) return rc;
+    }
+    const Plan pl = make_plan(p->batch, p->kv_heads, p->groups, p->comp_len, p->win_len, sm_count);
+    a.n_csplit = pl.n_csplit;
+    a.n_wsplit = pl.n_wsplit;
+    a.flat_ctas = pl.flat_ctas;
+    a.flat_q = pl.flat_q;
+    a.flat_r = pl.flat_r;
+    a.max_split = pl.max_split;
     a.slot_nz_bytes = pick_slot_nz_bytes(p);
     a.depth = pick_depth(a.slot_nz_bytes);
     auto s = static_cast<cudaStream_t>(stream);
     switch (p->groups) {
-        case 1: return launch_decode<1>(a, s);
-        case 2: return launch_decode<2>(a, s);
-        case 4: return launch_decode<4>(a, s);
-        default: return launch_decode<8>(a, s);
+        case 1: return a.flat_ctas > 0 ? launch_decode<1, true>(a, s) : launch_decode<1, false>(a, s);
+        case 2: return a.flat_ctas > 0 ? launch_decode<2, true>(a, s) : launch_decode<2, false>(a, s);
+        case 4: return a.flat_ctas > 0 ? launch_decode<4, true>(a, s) : launch_decode<4, false>(a, s);
+        default: return a.flat_ctas > 0 ? launch_decode<8, true>(a, s) : launch_decode<8, false>(a, s);
     }
 }
 
@@ -892,6 +1001,13 @@ extern "C" size_t mfb200_decode_workspace_max(int batch, int kv_heads, int group
     }
     size_t ws = 0;
     if (mfb200_decode_plan(batch, kv_heads, groups, max_comp_len - max_comp_len % 64, max_win_len > 0 ? max_win_len : 1, sm_count, &ws, nullptr) > 0 && ws > best) best = ws;
+    {   // closed-form bound on the partial slots per unit over all shorter contexts (splits never exceed slots/units + 2)
+        if (sm_count <= 0 && device_sm_count(&sm_count) != MFB200_OK) sm_count = 148;
+        const size_t units = static_cast<size_t>(batch) * kv_heads;
+        const size_t per_unit = static_cast<size_t>(sm_count) * 3 / units + 4 + (max_win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit;
+        const size_t bound = ((units * 4 + 255) & ~static_cast<size_t>(255)) + units * per_unit * groups * kPartStride * 4;
+        if (bound > best) best = bound;
+    }
     return best + 4096;
 }
 
@@ -902,9 +1018,7 @@ extern "C" int mfb200_decode_step(mfb200_decode_params* p, const void* q, const 
     p->out = out;
     p->k_new = k_new;
     p->v_new = v_new;
+    (void)sm_count;
     p->win_len += 1;
-    const int n = mfb200_decode_plan(p->batch, p->kv_heads, p->groups, p->comp_len, p->win_len, sm_count, nullptr, nullptr);
-    if (n < 0) return n;
-    p->n_split = n;
     return mfb200_sparse_decode_attention(p, stream);
 }

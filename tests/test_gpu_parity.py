@@ -326,6 +326,44 @@ def test_repeated_launches_are_stable_and_correct(b, hkv, groups, T, sparsity):
     assert d.max() <= MAX_ABS and d.mean() <= MEAN_ABS, (d.max(), d.mean())
 
 
+def test_flat_partition_mode():
+    """Mid-size launches use the flat work partition (all blocks of all units divided evenly over the resident
+    CTA slots; CTAs cross unit boundaries and process several segments).  Forced here on small shapes through the
+    MFB200_FLAT tuning override, plus one shape that selects it naturally; checked against the masked-dense oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = """
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from mustafar_b200.attention import MustafarKVCache
+from oracle import mustafar_oracle as O
+for (b, hkv, g, T, s) in SHAPES:
+    gen = torch.Generator().manual_seed(T + g)
+    k = torch.randn(b, hkv, T, 128, generator=gen).half(); v = torch.randn(b, hkv, T, 128, generator=gen).half()
+    q = torch.randn(b, hkv * g, 1, 128, generator=gen).half()
+    c = MustafarKVCache(b, hkv, g, T + 64, s, s); c.prefill(k.cuda(), v.cuda())
+    outs = [c.attend(q.cuda()).clone() for _ in range(3)]
+    torch.cuda.synchronize()
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    L = c.comp_len
+    kp = k.numpy().copy(); vp = v.numpy().copy()
+    kp[:, :, :L] = O.prune_rows(kp[:, :, :L], s); vp[:, :, :L] = O.prune_rows(vp[:, :, :L], s)
+    d = np.abs(outs[-1].float().cpu().numpy() - O.masked_dense_attention(q.numpy(), kp, vp).astype(np.float32))
+    assert d.max() <= 2e-3 and d.mean() <= 1e-3, (b, hkv, g, T, s, d.max(), d.mean())
+print("FLAT-OK")
+""" % root
+    cases = [("5", "[(1, 8, 1, 2112, 0.5), (1, 4, 4, 1312, 0.7)]"), ("12", "[(1, 8, 1, 2112, 0.5), (2, 4, 2, 1088, 0.5)]"),
+             ("37", "[(1, 8, 4, 2112, 0.7), (1, 8, 8, 1088, 0.5)]"), (None, "[(8, 16, 1, 4160, 0.7)]")]
+    for forced, shapes in cases:
+        env = dict(os.environ)
+        env.pop("MFB200_FLAT", None)
+        if forced is not None:
+            env["MFB200_FLAT"] = forced
+        r = subprocess.run([sys.executable, "-c", "SHAPES = " + shapes + code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "FLAT-OK" in r.stdout, (forced, r.stdout[-1500:] + r.stderr[-1500:])
+
+
 def test_no_uninitialised_shared_memory_reads():
     """Runs attention cases through the debug build whose CTAs start by filling their dynamic shared memory
     with fp16 NaNs (make poison): any read of uninitialised / not-yet-published shared memory turns the
