@@ -144,10 +144,10 @@ __host__ __device__ inline int unit_csplits(const DecodeArgs& a, int unit) {
 }
 
 // Writes this split's partial (o[G][128] from smem `ored`, m, l) into slot `split` of the unit and lets the last
-// of the unit's `n_split` contributors merge.
+// of the unit's `n_split` contributors merge.  All threads of the CTA must call it.
 template <int G>
 __device__ __forceinline__ void write_partial_and_merge(const DecodeArgs& a, int unit, int split, int n_split,
-                                                        const float* ored, const float* m, const float* l) {
+                                                        const float* ored, const float* m, const float* l, float* scratch) {
     const mfb200_decode_params& p = a.p;
     const int tid = threadIdx.x;
     const int units = p.batch * p.kv_heads;
@@ -169,18 +169,55 @@ __device__ __forceinline__ void write_partial_and_merge(const DecodeArgs& a, int
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // ---- merge (last contributor of the unit) -------------------------------------------------------------
+    // The merge sits on the launch's critical path (everyone else has already left), so it is organised for
+    // ONE global round trip: each warp folds a strided subset of the partials of one query head with all its
+    // loads in flight (128-bit, L2), then the per-warp results are combined through shared memory.
+    constexpr int kWpg = (G <= 2 ? kAttnWarps : 8) / G;  // warps per query head: 10, 5, 2, 1
+    // `scratch`: kAttnWarps * kPartStride floats of dynamic shared memory that is dead by now (may alias `ored`,
+    // which was consumed before the barriers above).  Per warp: o[128], m, den.
+    float (*s_red)[kPartStride] = reinterpret_cast<float (*)[kPartStride]>(scratch);
     const float* up = parts + static_cast<int64_t>(unit) * a.max_split * G * kPartStride;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp < kWpg * G) {
+        const int g = warp % G;
+        float m_run = -INFINITY, den = 0.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int s = warp / G; s < n_split; s += kWpg) {
+            const float* ps = up + (s * G + g) * kPartStride;
+            const float ms = __ldcg(ps + 128), ls = __ldcg(ps + 129);
+            const float4 o = __ldcg(reinterpret_cast<const float4*>(ps) + lane);
+            const float mn = fmaxf(m_run, ms);
+            // a partial with no visible token has m = -inf, l = 0, o = 0: weight it 0 (and avoid inf - inf)
+            const float so = (m_run == -INFINITY) ? 0.f : exp2f((m_run - mn) * kLog2e);
+            const float w = (ms == -INFINITY) ? 0.f : exp2f((ms - mn) * kLog2e);
+            den = den * so + ls * w;
+            acc.x = acc.x * so + o.x * w;
+            acc.y = acc.y * so + o.y * w;
+            acc.z = acc.z * so + o.z * w;
+            acc.w = acc.w * so + o.w * w;
+            m_run = mn;
+        }
+        reinterpret_cast<float4*>(s_red[warp])[lane] = acc;
+        if (lane == 0) {
+            s_red[warp][128] = m_run;
+            s_red[warp][129] = den;
+        }
+    }
+    __syncthreads();
     for (int i = tid; i < G * 128; i += kAttnThreads) {
         const int g = i >> 7, c = i & 127;
         float mx = -INFINITY;
-        for (int s = 0; s < n_split; ++s) mx = fmaxf(mx, __ldcg(up + (s * G + g) * kPartStride + 128));
+#pragma unroll
+        for (int j = 0; j < kWpg; ++j) mx = fmaxf(mx, s_red[j * G + g][128]);
         float den = 0.f, num = 0.f;
-        for (int s = 0; s < n_split; ++s) {
-            const float* ps = up + (s * G + g) * kPartStride;
-            const float ms = __ldcg(ps + 128);
-            const float w = (ms == -INFINITY) ? 0.f : exp2f((ms - mx) * kLog2e);
-            den += __ldcg(ps + 129) * w;
-            num += __ldcg(ps + c) * w;
+#pragma unroll
+        for (int j = 0; j < kWpg; ++j) {
+            const float mj = s_red[j * G + g][128];
+            const float w = (mj == -INFINITY) ? 0.f : exp2f((mj - mx) * kLog2e);
+            den += s_red[j * G + g][129] * w;
+            num += s_red[j * G + g][c] * w;
         }
         const int64_t qh = static_cast<int64_t>(unit) * G + g;  // = b*Hq + h*G + g
         static_cast<__half*>(p.out)[qh * kHeadDim + c] = __float2half_rn(num / den);
@@ -571,7 +608,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         ored[i] = red[((2 * hf) * G + g) * 64 + e] + red[((2 * hf + 1) * G + g) * 64 + e];
     }
     __syncthreads();
-    write_partial_and_merge<G>(a, unit, split, n_split, ored, stat, stat + 8);
+    write_partial_and_merge<G>(a, unit, split, n_split, ored, stat, stat + 8, reinterpret_cast<float*>(smem));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -761,7 +798,7 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
         ored[i] = s;
     }
     __syncthreads();
-    write_partial_and_merge<G>(a, unit, split, n_split, ored, ml, ml + 8);
+    write_partial_and_merge<G>(a, unit, split, n_split, ored, ml, ml + 8, reinterpret_cast<float*>(smem));
 }
 
 // FLAT is a compile-time switch so that the uniform-mode kernel carries no segment-loop state in registers.
