@@ -48,7 +48,8 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 struct DecodeArgs {
     mfb200_decode_params p;
-    int n_csplit;   // uniform mode: compressed splits per unit
+    int n_csplit;   // uniform mode: compressed splits per unit ...
+    int n_extra;    //   ... plus one for the units u < n_extra (so that the CTA count can match the resident slots)
     int n_wsplit;   // window chunks per unit
     int flat_ctas;  // flat mode (> 0): number of compressed CTAs n; they partition the B = units*nblk blocks evenly:
     int flat_q;     //   B / n   -> CTA c owns global blocks [c*q + min(c, r), ...) : q + 1 blocks if c < r, else q
@@ -113,6 +114,27 @@ __host__ __device__ inline SmemMap smem_map(int G, int slot_nz_bytes, int depth)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Timeline instrumentation (`make trace`, tools/trace_attn.py): per-CTA phase timestamps from %globaltimer.
+#ifdef MFB_TRACE
+constexpr int kTraceSlots = 16, kTraceMaxCtas = 8192;
+__device__ unsigned long long g_trace[2 * kTraceMaxCtas * kTraceSlots];  // two launches: params.reserved & 1 picks the half
+__shared__ int s_trace_half;  // set by thread 0 at kernel entry (barriers follow before any other thread traces)
+__device__ __forceinline__ void trace_val(int k, unsigned long long v) {
+    const int s_half = s_trace_half;
+    if (blockIdx.x < kTraceMaxCtas) g_trace[(static_cast<size_t>(s_half) * kTraceMaxCtas + blockIdx.x) * kTraceSlots + k] = v;
+}
+__device__ __forceinline__ void trace_at(int k) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace_val(k, t);
+}
+#define MFB_TRACE_AT(k) trace_at(k)
+#define MFB_TRACE_VAL(k, v) trace_val(k, v)
+#else
+#define MFB_TRACE_AT(k) ((void)0)
+#define MFB_TRACE_VAL(k, v) ((void)0)
+#endif
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -138,7 +160,7 @@ __host__ __device__ inline uint32_t flat_owner(const DecodeArgs& a, uint32_t x) 
 }
 // number of compressed partials of `unit`
 __host__ __device__ inline int unit_csplits(const DecodeArgs& a, int unit) {
-    if (a.flat_ctas <= 0) return a.n_csplit;
+    if (a.flat_ctas <= 0) return a.n_csplit + (unit < a.n_extra ? 1 : 0);
     const uint32_t nblk = a.p.comp_len / kBlockTokens;
     return static_cast<int>(flat_owner(a, (unit + 1) * nblk - 1) - flat_owner(a, unit * nblk)) + 1;
 }
@@ -160,15 +182,20 @@ __device__ __forceinline__ void write_partial_and_merge(const DecodeArgs& a, int
         mine[tid * kPartStride + 129] = l[tid];
     }
     __shared__ int s_last;
-    __threadfence();
+    // Release/acquire through the ticket: the CTA's partial stores happen-before thread 0's release (bar.sync), and
+    // thread 0's acquire happens-before the merge loads of the whole CTA (bar.sync) - no full fences needed.
     __syncthreads();
     if (tid == 0) {
-        const int ticket = atomicAdd(&counters[unit], 1);
+        int ticket;
+        asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(ticket) : "l"(&counters[unit]) : "memory");
         s_last = (ticket == n_split - 1);
     }
     __syncthreads();
+    if (tid == 0) {
+        MFB_TRACE_AT(9);
+        MFB_TRACE_VAL(13, static_cast<unsigned long long>(s_last));
+    }
     if (!s_last) return;
-    __threadfence();
     // ---- merge (last contributor of the unit) -------------------------------------------------------------
     // The merge sits on the launch's critical path (everyone else has already left), so it is organised for
     // ONE global round trip: each warp folds a strided subset of the partials of one query head with all its
@@ -335,6 +362,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         }
     }
     __syncthreads();
+    if (tid == 0) MFB_TRACE_AT(1);
     const uint8_t* k_nz = static_cast<const uint8_t*>(p.k_nz) + p.k_nz_off[unit] * 16;
     const uint8_t* v_nz = static_cast<const uint8_t*>(p.v_nz) + p.v_nz_off[unit] * 16;
     const uint64_t* k_bmp = p.k_bmp + static_cast<int64_t>(unit) * p.bmp_stride + static_cast<int64_t>(blk0) * 128;
@@ -365,11 +393,16 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     const bool is_producer = (warp == kWarpProducer) && (lane == 0);
     if (is_producer) produce_until(nb < D ? nb : D);  // first ring-full: never blocks
     if (early_kv) pdl_wait_prior_grids();
+    if (tid == 0) MFB_TRACE_AT(2);
     {
         const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
         for (int i = tid; i < G * kHeadDim; i += kAttnThreads) qs[(i & 127) * G + (i >> 7)] = q[i];
     }
     __syncthreads();  // q staged (threads of every warp contribute) before the K warps read it
+    if (tid == 0) {
+        MFB_TRACE_AT(3);
+        MFB_TRACE_VAL(12, static_cast<unsigned long long>(nb));
+    }
     float o_acc[G][2];
 #pragma unroll
     for (int g = 0; g < G; ++g) o_acc[g][0] = o_acc[g][1] = 0.f;
@@ -554,6 +587,8 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                 for (int g = 0; g < G; ++g) *reinterpret_cast<float2*>(sp + g * 64 + 2 * lane) = make_float2(sc[g][0], sc[g][1]);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[Bars::kScFull + buf]);
+                if (tid == 0 && n == 0) MFB_TRACE_AT(4);
+                if (tid == 0 && n == nb - 1) MFB_TRACE_AT(5);
             } else {
                 // V item: tiles 32w .. 32w+31 = channel half (w>>1), tokens 32*(w&1)+j -> channels (2*lane, 2*lane+1)
                 mbar_wait(&bars[Bars::kPFull + buf], par2);
@@ -569,6 +604,8 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                     mbar_arrive(&bars[empty0 + s]);
                     mbar_arrive(&bars[Bars::kPEmpty + buf]);
                 }
+                if (tid == kWarpV0 * 32 && n == 0) MFB_TRACE_AT(6);
+                if (tid == kWarpV0 * 32 && n == nb - 1) MFB_TRACE_AT(7);
             }
         }
         if constexpr (G >= 4) {
@@ -587,6 +624,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     }
     // ---- cross-warp reduction of o: V warps (0,1) hold channel half 0, (2,3) half 1 -------------------
     __syncthreads();
+    if (tid == 0) MFB_TRACE_AT(8);
     float* red = spart;                                          // [4][G][64]
     float* ored = reinterpret_cast<float*>(smem + sm.slots_k);   // [G][128] (the rings are idle now)
     if (warp >= kWarpV0 && warp < kWarpV0 + kTileWarps) {
@@ -616,6 +654,11 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
 // The chunk's K rows and V rows are contiguous (64 x 256 B each): one elected thread fetches both with
 // two bulk copies at kernel entry, so the whole split costs a single DRAM round trip; scores, softmax
 // and P.V then run out of shared memory.  Uses the first 8 warps of the CTA.
+// q in the window path: a lane reads the 8-channel chunks `seg` and `8 + seg` of every head, the 8 lanes of a token
+// differ in seg -> a chunk pitch of 9 floats spreads them over distinct banks (a [channel][G] layout made every
+// such load an 8-way conflict: 7 % of all shared-memory wavefronts of a GQA launch).
+constexpr int kWinQPitch = 16 * 9;
+__device__ __forceinline__ int win_q_index(int g, int c) { return g * kWinQPitch + (c >> 3) * 9 + (c & 7); }
 struct WinSmem {
     uint32_t kw, vw, bar, qs, sw, red, ored, ml, total;
 };
@@ -628,8 +671,8 @@ __host__ __device__ inline WinSmem win_smem_map(int G) {
     o += kWinTokensPerSplit * kHeadDim * 2;
     m.bar = o;
     o += 16;
-    m.qs = o;  // float [128][G]
-    o += kHeadDim * G * 4;
+    m.qs = o;  // float [G][16 chunks of 8 channels, pitch 9]: see win_q_index
+    o += G * kWinQPitch * 4;
     m.sw = o;  // float [G][64] scores, then probabilities
     o += G * kWinTokensPerSplit * 4;
     m.red = o;  // float [8 warps][G][128]
@@ -677,7 +720,7 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
     }
     {
         const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
-        for (int i = tid; i < G * kHeadDim; i += kAttnThreads) qs[(i & 127) * G + (i >> 7)] = __half2float(q[i]);
+        for (int i = tid; i < G * kHeadDim; i += kAttnThreads) qs[win_q_index(i >> 7, i & 127)] = __half2float(q[i]);
     }
     __syncthreads();  // q staged, barrier initialised
     mbar_wait(bar, 0);
@@ -706,8 +749,8 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
         for (int g = 0; g < G; ++g)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                qr[g][i] = qs[(8 * seg + i) * G + g];
-                qr[g][8 + i] = qs[(64 + 8 * seg + i) * G + g];
+                qr[g][i] = qs[win_q_index(g, 8 * seg + i)];
+                qr[g][8 + i] = qs[win_q_index(g, 64 + 8 * seg + i)];
             }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -814,15 +857,26 @@ __global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 
         __syncthreads();
     }
 #endif
+    if (threadIdx.x == 0) {
+#ifdef MFB_TRACE
+        s_trace_half = a.p.reserved & 1;
+#endif
+        MFB_TRACE_AT(0);
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        MFB_TRACE_VAL(11, smid);
+        MFB_TRACE_VAL(12, ~0ull);  // window CTA unless overwritten
+    }
     const int units = a.p.batch * a.p.kv_heads;
     const int nblk = a.p.comp_len / kBlockTokens;
     const int id = blockIdx.x;
-    const int n_comp = FLAT ? a.flat_ctas : a.n_csplit * units;
+    const int n_base = a.n_csplit * units;  // uniform mode: CTAs [0, n_base) = split-major, then one extra split for units < n_extra
+    const int n_comp = FLAT ? a.flat_ctas : n_base + a.n_extra;
     if (id < n_comp) {
         if constexpr (!FLAT) {  // uniform mode: split `id / units` of unit `id % units`
-            const int unit = id % units, split = id / units;
-            compressed_split<G>(a, smem, unit, split, a.n_csplit + a.n_wsplit, split * nblk / a.n_csplit,
-                                (split + 1) * nblk / a.n_csplit, false);
+            const int unit = id < n_base ? id % units : id - n_base, split = id < n_base ? id / units : a.n_csplit;
+            const int nc = unit_csplits(a, unit);
+            compressed_split<G>(a, smem, unit, split, nc + a.n_wsplit, split * nblk / nc, (split + 1) * nblk / nc, false);
         } else {
             // flat mode: an even cut of all units*nblk blocks, processed as segments cut at unit boundaries (one partial
             // per segment).  The segment arithmetic is redone per segment from opaque copies of (id, j) so that nothing
@@ -843,9 +897,10 @@ __global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 
         }
     } else {  // dense-window chunks come after all compressed CTAs
         const int unit = (id - n_comp) % units, wchunk = (id - n_comp) / units;
-        const int nc = FLAT ? unit_csplits(a, unit) : a.n_csplit;
+        const int nc = unit_csplits(a, unit);
         window_split<G>(a, smem, unit, nc + wchunk, nc + a.n_wsplit, wchunk);
     }
+    if (threadIdx.x == 0) MFB_TRACE_AT(10);
 }
 
 static size_t window_smem_bytes(int G) { return win_smem_map(G).total; }
@@ -862,7 +917,7 @@ static int pick_depth(int slot_nz_bytes) { return slot_nz_bytes <= 8 * 1024 ? 3 
 template <int G, bool FLAT>
 static int launch_decode(const DecodeArgs& a, cudaStream_t s) {
     const SmemMap sm = smem_map(G, a.slot_nz_bytes, a.depth);
-    size_t smem = (a.n_csplit > 0 || a.flat_ctas > 0) ? sm.total : 0;
+    size_t smem = (a.n_csplit > 0 || a.n_extra > 0 || a.flat_ctas > 0) ? sm.total : 0;
     if (a.n_wsplit > 0) smem = smem > window_smem_bytes(G) ? smem : window_smem_bytes(G);
     static size_t configured = 0;
     if (smem > configured) {
@@ -872,7 +927,7 @@ static int launch_decode(const DecodeArgs& a, cudaStream_t s) {
     }
     cudaLaunchConfig_t cfg = {};
     const int units = a.p.batch * a.p.kv_heads;
-    cfg.gridDim = dim3((a.flat_ctas > 0 ? a.flat_ctas : a.n_csplit * units) + a.n_wsplit * units);
+    cfg.gridDim = dim3((a.flat_ctas > 0 ? a.flat_ctas : a.n_csplit * units + a.n_extra) + a.n_wsplit * units);
     cfg.blockDim = dim3(kAttnThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
@@ -891,7 +946,7 @@ using namespace mfb;
 
 namespace mfb {
 struct Plan {
-    int n_csplit, n_wsplit, flat_ctas, flat_q, flat_r, max_split;
+    int n_csplit, n_extra, n_wsplit, flat_ctas, flat_q, flat_r, max_split;
 };
 // Work decomposition of one launch.  Every CTA of a small launch should be resident at once (a second, nearly
 // empty wave doubles the time of a batch-1 launch); window CTAs are short and dispatched last, so only a
@@ -900,7 +955,7 @@ struct Plan {
 //  * flat mode (24..256 blocks per CTA): the launch's units*nblk blocks are divided evenly over exactly the
 //    resident CTA slots, CTAs may cross unit boundaries -> no wave-quantisation loss for mid-size batches.
 static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count) {
-    Plan pl = {0, (win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit, 0, 0, 0, 0};
+    Plan pl = {0, 0, (win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit, 0, 0, 0, 0};
     const int64_t units = static_cast<int64_t>(batch) * kv_heads;
     const int nblk = comp_len / kBlockTokens;
     if (nblk > 0) {
@@ -928,13 +983,17 @@ static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win
             pl.max_split = (nblk + pl.flat_q - 1) / pl.flat_q + 1 + pl.n_wsplit;
             return pl;
         }
-        int64_t per_unit = avail / units;
+        static const int forced_target = [] { const char* e = getenv("MFB200_TARGET_CTAS"); return e ? atoi(e) : 0; }();
+        const int64_t target = forced_target > 0 ? forced_target : avail;  // compressed CTAs of a uniform-mode launch
+        int64_t per_unit = target / units;
         const int min_c = (nblk + kMaxBlocksPerSplit - 1) / kMaxBlocksPerSplit;
         if (per_unit < min_c) per_unit = min_c;
         if (per_unit > nblk) per_unit = nblk;
         pl.n_csplit = static_cast<int>(per_unit);
+        // spend the remaining slots on one more split for the first units (no unit is ever cut finer than a block)
+        if (per_unit == target / units && per_unit < nblk) pl.n_extra = static_cast<int>(target % units);
     }
-    pl.max_split = pl.n_csplit + pl.n_wsplit;
+    pl.max_split = pl.n_csplit + (pl.n_extra > 0 ? 1 : 0) + pl.n_wsplit;
     return pl;
 }
 static int device_sm_count(int* out) {
@@ -1010,6 +1069,7 @@ extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb
     }
     const Plan pl = make_plan(p->batch, p->kv_heads, p->groups, p->comp_len, p->win_len, sm_count);
     a.n_csplit = pl.n_csplit;
+    a.n_extra = pl.n_extra;
     a.n_wsplit = pl.n_wsplit;
     a.flat_ctas = pl.flat_ctas;
     a.flat_q = pl.flat_q;
@@ -1059,3 +1119,15 @@ extern "C" int mfb200_decode_step(mfb200_decode_params* p, const void* q, const 
     p->win_len += 1;
     return mfb200_sparse_decode_attention(p, stream);
 }
+
+#ifdef MFB_TRACE
+// debug build only: copies the last launch's per-CTA timeline (kTraceSlots u64 per CTA) to the host
+extern "C" int mfb200_debug_trace(unsigned long long* out, int n_ctas) {
+    if (n_ctas > mfb::kTraceMaxCtas) n_ctas = mfb::kTraceMaxCtas;
+    MFB_CUDA(cudaMemcpyFromSymbol(out, mfb::g_trace, sizeof(unsigned long long) * mfb::kTraceSlots * n_ctas));
+    MFB_CUDA(cudaMemcpyFromSymbol(out + static_cast<size_t>(mfb::kTraceSlots) * n_ctas, mfb::g_trace,
+                                  sizeof(unsigned long long) * mfb::kTraceSlots * n_ctas,
+                                  sizeof(unsigned long long) * mfb::kTraceSlots * mfb::kTraceMaxCtas));
+    return mfb::kTraceSlots;
+}
+#endif
