@@ -102,6 +102,20 @@ int mfb200_compress_append_chunk(void* k_win, void* v_win, int64_t win_stride, i
                                  int64_t tile_offset, int64_t head_capacity, int32_t* overflow,
                                  mfb200_stream_t stream);
 
+/* Prefill (models/llama_mustafar_kernel.py:416-442: dh_prune_key/value + convert_key/value_batched on the prompt):
+ * prunes and compresses tokens [0, tokens) of key_states / value_states (fp16 [batch, kv_heads, >= tokens, 128],
+ * arbitrary batch / head / token strides given in halves as {stride_b, stride_h, stride_t}, innermost stride 1)
+ * into the cache slabs at tile_offset, K and V in ONE single-pass launch (each input element is read once; block
+ * offsets are exchanged between CTAs with a decoupled look-back).  status_ws: 2 * batch * kv_heads * tokens/64 * 8
+ * bytes of scratch (zeroed by the call).  Slabs / head_base / head_capacity / overflow as in
+ * mfb200_compress_append_chunk.  Bit-identical to mfb200_compress_count + _scan + _pack. */
+int mfb200_compress_prefill(const void* k, const void* v, const int64_t* k_strides, const int64_t* v_strides,
+                            int batch, int kv_heads, int64_t tokens, int prune_k_key, int prune_k_value,
+                            int64_t* k_bmp, int32_t* k_idx, void* k_nz, const int64_t* k_head_base,
+                            int64_t* v_bmp, int32_t* v_idx, void* v_nz, const int64_t* v_head_base,
+                            int64_t bmp_stride, int64_t idx_stride, int64_t tile_offset, int64_t head_capacity,
+                            int32_t* overflow, void* status_ws, mfb200_stream_t stream);
+
 /* ---- a8-a13: the two batched SpMV operators, reference argument order ----------------------------------
  * C[bq, n, m] (fp16 [Batch_Size, 8, M_Global]).  N_Global must be 8, K_Global 128 (key) /
  * M_Global 128 (value), Split_K is ignored (the reference hard-wires 1).  `A` is unused (NULL in the

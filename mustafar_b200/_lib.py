@@ -51,6 +51,8 @@ SIGNATURES = {
     "mfb200_compress_pack": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),
     "mfb200_compress_append_chunk": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                             _i64, _i64, _i64, _i64, _vp, _vp]),
+    "mfb200_compress_prefill": (_i32, [_vp, _vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _i32, _i32, _i64, _i32, _i32,
+                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "mfb200_key_formulation": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32]),
     "mfb200_value_formulation": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32]),
     "mfb200_value_workspace_bytes": (C.c_size_t, [_i32, _i32]),

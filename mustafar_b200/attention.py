@@ -24,7 +24,6 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .compression import compress_into, pack_into
 from .pruning import HEAD_DIM, prune_rank
 
 COMPRESS_CHUNK = 256  # llama_mustafar_kernel.py:324
@@ -81,10 +80,9 @@ class MustafarKVCache:
             self.k_win = torch.zeros((self.units, self.win_cap, HEAD_DIM), dtype=torch.float16, device=self.device)
             self.v_win = torch.zeros_like(self.k_win)
             self.overflow = torch.zeros((1,), dtype=torch.int32, device=self.device)
-            self._tmp_bmp = torch.empty((self.units, COMPRESS_CHUNK * 2), dtype=torch.int64, device=self.device)
-            self._tmp_cnt = torch.empty((self.units, COMPRESS_CHUNK * 2), dtype=torch.int32, device=self.device)
         self.comp_len = 0
         self.win_len = 0
+        self._prefill_status = None
         self._ws = None
         self._ws_bytes = 0
         self._plan_cache = {}
@@ -106,23 +104,29 @@ class MustafarKVCache:
         return self.comp_len + self.win_len
 
     # ------------------------------------------------------------------ compression
-    def _compress_rows(self, stream: _Stream, x: torch.Tensor, layout: int, sparsity: float):
-        """Prune + compress x [units, M, 128] and append it at token offset self.comp_len."""
+    def _compress_prompt(self, key_states: torch.Tensor, value_states: torch.Tensor, L: int):
+        """Prune + compress tokens [0, L) of the prompt, K and V, with ONE single-pass launch
+        (`mfb200_compress_prefill`); the inputs are read in place through their strides."""
         self._streams_dirty = True
-        units, m, _ = x.shape
-        tile_off = self.comp_len * 2
-        if m * 2 > self._tmp_bmp.shape[1]:
-            bmp_tmp = torch.empty((units, m * 2), dtype=torch.int64, device=self.device)
-            cnt_tmp = torch.empty((units, m * 2), dtype=torch.int32, device=self.device)
-        else:
-            bmp_tmp = self._tmp_bmp[:, : m * 2] if m * 2 == self._tmp_bmp.shape[1] else torch.empty(
-                (units, m * 2), dtype=torch.int64, device=self.device)
-            cnt_tmp = self._tmp_cnt[:, : m * 2] if m * 2 == self._tmp_cnt.shape[1] else torch.empty(
-                (units, m * 2), dtype=torch.int32, device=self.device)
-        compress_into(x, layout, prune_rank(sparsity), bmp_tmp, cnt_tmp, stream.idx, stream.cap_tiles + 1, tile_off, None)
-        pack_into(x, layout, bmp_tmp, stream.idx, stream.cap_tiles + 1, tile_off, stream.head_base, stream.nz,
-                  stream.head_capacity, self.overflow)
-        stream.bmp[:, tile_off: tile_off + m * 2].copy_(bmp_tmp)
+
+        def strided(x):
+            ok = (x.dtype == torch.float16 and x.stride(3) == 1 and x.data_ptr() % 8 == 0
+                  and all(st % 4 == 0 for st in x.stride()[:3]))
+            x = x if ok else x.contiguous()
+            return x, (C.c_int64 * 3)(x.stride(0), x.stride(1), x.stride(2))
+
+        k, ks = strided(key_states)
+        v, vs = strided(value_states)
+        nblk = L // 64
+        if self._prefill_status is None or self._prefill_status.numel() < 2 * self.units * nblk:
+            self._prefill_status = torch.empty(2 * self.units * nblk, dtype=torch.int64, device=self.device)
+        sk, sv = self.k, self.v
+        _lib.check(_lib.load().mfb200_compress_prefill(
+            k.data_ptr(), v.data_ptr(), ks, vs, self.batch, self.kv_heads, L, prune_rank(self.k_sparsity),
+            prune_rank(self.v_sparsity), sk.bmp.data_ptr(), sk.idx.data_ptr(), sk.nz.data_ptr(), sk.head_base.data_ptr(),
+            sv.bmp.data_ptr(), sv.idx.data_ptr(), sv.nz.data_ptr(), sv.head_base.data_ptr(), sk.cap_tiles, sk.cap_tiles + 1,
+            self.comp_len * 2, min(sk.head_capacity, sv.head_capacity), self.overflow.data_ptr(), self._prefill_status.data_ptr(),
+            _lib.stream_ptr()), "mfb200_compress_prefill")
 
     def prefill(self, key_states: torch.Tensor, value_states: torch.Tensor):
         """key/value_states: fp16 [B, Hkv, T, 128] (post-RoPE).  llama_mustafar_kernel.py:416-442."""
@@ -132,10 +136,7 @@ class MustafarKVCache:
         self.comp_len = 0
         with torch.cuda.device(self.device):
             if L > 0:
-                self._compress_rows(self.k, key_states[:, :, :L].reshape(self.units, L, d).contiguous(), _lib.LAYOUT_KEY,
-                                    self.k_sparsity)
-                self._compress_rows(self.v, value_states[:, :, :L].reshape(self.units, L, d).contiguous(),
-                                    _lib.LAYOUT_VALUE, self.v_sparsity)
+                self._compress_prompt(key_states, value_states, L)
             self.comp_len = L
             lw = t - L
             assert lw <= self.win_cap

@@ -344,6 +344,176 @@ __global__ void __launch_bounds__(kChunkThreads) compress_append_chunk_kernel(co
 }
 constexpr size_t kChunkSmem = kChunkTokens * kPitch * 2 + 3 * kChunkTiles * 4 + 32 * 64 * 2;
 
+// ---- prefill: prune + compress a whole prompt, K and V, in ONE single-pass launch ----------------------------
+// (models/llama_mustafar_kernel.py:416-442: dh_prune_* + convert_*_batched on the prompt.)  CTA = one 64-token
+// block of one (unit, K|V): the block is read once (strided source, no .contiguous() copy), pruned in registers,
+// turned into bitmaps + padded counts, and packed straight into the cache slabs.  The packed offset of a block
+// is the sum of the padded counts of all earlier blocks of the unit; instead of a count pass + scan pass + a
+// second read of the input, blocks exchange that sum with a decoupled look-back (Merrill & Garland): each CTA
+// publishes its aggregate as soon as it is known, then warp 0 walks back over the predecessors' status words
+// (32 per probe) until it meets an inclusive prefix.  Predecessors have smaller linear CTA indices, so they
+// were dispatched earlier and are either finished or running: the wait cannot deadlock.
+// Algorithmic bytes per token-head and stream: 256 read + 16 bitmap + 8 idx + the padded nonzeros written.
+struct PrefillArgs {
+    const __half* x[2];                   // key_states, value_states: [B, Hkv, tokens, 128], innermost stride 1
+    int64_t stride_b[2], stride_h[2], stride_t[2];  // halves
+    int kv_heads;
+    int prune_k[2];
+    int64_t* bmp[2];
+    int32_t* idx[2];
+    __half* nz[2];
+    const int64_t* head_base[2];
+    int64_t bmp_stride, idx_stride, tile_offset, head_capacity;
+    int32_t* overflow;
+    unsigned long long* status;           // [2][units][blocks], zeroed by the host: (state << 32) | value
+};
+constexpr unsigned long long kStAggregate = 1ull << 32, kStPrefix = 2ull << 32;
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Warp-collective.  Returns the exclusive prefix of block `tb` (= carry + totals of blocks 0..tb-1) and publishes
+// this block's status.  The status word carries its own payload, so relaxed (L2-coherent) accesses are enough.
+__device__ __forceinline__ int32_t lookback_exclusive(unsigned long long* st, int tb, int32_t total, int32_t carry) {
+    const uint32_t lane = lane_id();
+    if (lane == 0) st_relaxed_u64(&st[tb], kStAggregate | static_cast<uint32_t>(total));
+    int32_t excl = 0;
+    for (int look = tb - 1;; look -= 32) {
+        const int j = look - static_cast<int>(lane);
+        unsigned long long s;
+        while (true) {  // block -1 is a virtual predecessor whose inclusive prefix is the unit's carry-in
+            s = j >= 0 ? ld_relaxed_u64(&st[j]) : (kStPrefix | static_cast<uint32_t>(j == -1 ? carry : 0));
+            if (!__any_sync(0xffffffffu, (s >> 32) == 0)) break;
+            __nanosleep(40);
+        }
+        const int32_t val = static_cast<int32_t>(static_cast<uint32_t>(s));
+        const uint32_t pm = __ballot_sync(0xffffffffu, (s >> 32) == 2);
+        if (pm) {  // nearest inclusive prefix: add the aggregates in front of it and stop
+            const uint32_t first = __ffs(pm) - 1;
+            excl += __reduce_add_sync(0xffffffffu, lane <= first ? val : 0);
+            break;
+        }
+        excl += __reduce_add_sync(0xffffffffu, val);
+    }
+    if (lane == 0) st_relaxed_u64(&st[tb], kStPrefix | static_cast<uint32_t>(excl + total));
+    return excl;
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ void prefill_block_body(const PrefillArgs& a, int which, uint16_t* tile, uint32_t* bm_hi,
+                                                   uint32_t* bm_lo, uint16_t (*stage)[64]) {
+    __shared__ int32_t warp_tot[8];
+    __shared__ int32_t s_excl;
+    const int tb = blockIdx.x;
+    const int64_t u = blockIdx.y, units = gridDim.y, nblk = gridDim.x;
+    const uint32_t lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    // 1. load + prune: warp w owns token rows 8w .. 8w+7 of the block
+    {
+        const __half* src = a.x[which] + (u / a.kv_heads) * a.stride_b[which] + (u % a.kv_heads) * a.stride_h[which] +
+                            static_cast<int64_t>(tb) * 64 * a.stride_t[which];
+        uint2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ldg_stream_v2(reinterpret_cast<const uint2*>(src + (warp * 8 + i) * a.stride_t[which]) + lane);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (a.prune_k[which] > 0) v[i] = prune4(v[i], a.prune_k[which]);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(tile + (warp * 8 + i) * kPitch + 4 * lane);
+            dst[0] = v[i].x;
+            dst[1] = v[i].y;
+        }
+    }
+    __syncthreads();
+    // 2. bitmaps + padded counts: warp w owns tiles 16w .. 16w+15, lane i < 16 keeps tile 16w+i
+    const int t0 = warp * 16;
+    uint32_t my_hi = 0, my_lo = 0;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        uint32_t e0, e1;
+        tile_elems<LAYOUT>(tile, t0 + i, lane, e0, e1);
+        const uint32_t hi = __brev(__ballot_sync(0xffffffffu, (e0 & 0x7fffu) != 0));
+        const uint32_t lo = __brev(__ballot_sync(0xffffffffu, (e1 & 0x7fffu) != 0));
+        if (lane == static_cast<uint32_t>(i)) {
+            my_hi = hi;
+            my_lo = lo;
+        }
+    }
+    const int64_t tile_g = a.tile_offset + static_cast<int64_t>(tb) * 128 + t0 + lane;  // lanes < 16
+    int32_t cnt = 0;
+    if (lane < 16) {
+        bm_hi[t0 + lane] = my_hi;
+        bm_lo[t0 + lane] = my_lo;
+        a.bmp[which][u * a.bmp_stride + tile_g] = static_cast<int64_t>((static_cast<uint64_t>(my_hi) << 32) | my_lo);
+        cnt = ((__popc(my_hi) + __popc(my_lo) + 7) & ~7) >> 1;
+    }
+    int32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= static_cast<uint32_t>(o)) incl += n;
+    }
+    if (lane == 15) warp_tot[warp] = incl;
+    __syncthreads();
+    // 3. this block's offset inside the unit's packed stream
+    int32_t* idx = a.idx[which] + u * a.idx_stride;
+    if (warp == 0) {
+        int32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) total += warp_tot[w];
+        const int32_t carry = a.tile_offset > 0 ? idx[a.tile_offset] : 0;
+        unsigned long long* st = a.status + (static_cast<int64_t>(which) * units + u) * nblk;
+        const int32_t excl = lookback_exclusive(st, tb, total, carry);
+        if (lane == 0) {
+            s_excl = excl;
+            if (tb == 0 && a.tile_offset == 0) idx[0] = 0;
+        }
+    }
+    __syncthreads();
+    int32_t base = s_excl;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    if (lane < 16) idx[tile_g + 1] = base + incl;
+    const int32_t my_off = base + incl - cnt;  // lanes < 16: offset of tile t0 + lane (2-half units)
+    // 4. pack: one contiguous (<= 128 B) store per tile
+    const uint32_t above = lane == 0 ? 0u : (0xffffffffu << (32 - lane));
+    const uint32_t mybit = 0x80000000u >> lane;
+    uint16_t* out = reinterpret_cast<uint16_t*>(a.nz[which]) + a.head_base[which][u];
+    uint32_t* st32 = reinterpret_cast<uint32_t*>(stage[warp]);
+#pragma unroll 2
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t hi = __shfl_sync(0xffffffffu, my_hi, i), lo = __shfl_sync(0xffffffffu, my_lo, i);
+        const int32_t o2 = __shfl_sync(0xffffffffu, my_off, i);
+        uint32_t e0, e1;
+        tile_elems<LAYOUT>(tile, t0 + i, lane, e0, e1);
+        st32[lane] = 0;
+        __syncwarp();
+        const uint32_t pc_hi = __popc(hi);
+        if (hi & mybit) stage[warp][__popc(hi & above)] = static_cast<uint16_t>(e0);
+        if (lo & mybit) stage[warp][pc_hi + __popc(lo & above)] = static_cast<uint16_t>(e1);
+        __syncwarp();
+        const uint32_t n_pad = (pc_hi + __popc(lo) + 7u) & ~7u;
+        if (a.head_capacity > 0 && 2 * static_cast<int64_t>(o2) + n_pad > a.head_capacity) {
+            if (lane == 0 && a.overflow != nullptr) atomicExch(a.overflow, 1);
+        } else if (2 * lane < n_pad) {
+            reinterpret_cast<uint32_t*>(out + 2 * static_cast<int64_t>(o2))[lane] = st32[lane];
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kCompressThreads) compress_prefill_kernel(const PrefillArgs a) {
+    __shared__ __align__(16) uint16_t tile[64 * kPitch];
+    __shared__ __align__(16) uint16_t stage[8][64];
+    __shared__ uint32_t bm_hi[128], bm_lo[128];
+    if (blockIdx.z == 0) prefill_block_body<MFB200_LAYOUT_KEY>(a, 0, tile, bm_hi, bm_lo, stage);
+    else prefill_block_body<MFB200_LAYOUT_VALUE>(a, 1, tile, bm_hi, bm_lo, stage);
+}
+
 // ---- window append: win[u, pos, :] = row[u, :] (K and V in one launch) -------------------------
 __global__ void __launch_bounds__(256)
 window_append_kernel(uint4* __restrict__ k_win, uint4* __restrict__ v_win, int64_t win_stride_v4,
@@ -486,4 +656,59 @@ extern "C" int mfb200_compress_append_chunk(void* k_win, void* v_win, int64_t wi
     dim3 grid(static_cast<unsigned>(units), 2);
     compress_append_chunk_kernel<<<grid, kChunkThreads, kChunkSmem, static_cast<cudaStream_t>(stream)>>>(a);
     return launch_status("compress_append_chunk_kernel");
+}
+
+extern "C" int mfb200_compress_prefill(const void* k, const void* v, const int64_t* k_strides, const int64_t* v_strides,
+                                       int batch, int kv_heads, int64_t tokens, int prune_k_key, int prune_k_value,
+                                       int64_t* k_bmp, int32_t* k_idx, void* k_nz, const int64_t* k_head_base,
+                                       int64_t* v_bmp, int32_t* v_idx, void* v_nz, const int64_t* v_head_base,
+                                       int64_t bmp_stride, int64_t idx_stride, int64_t tile_offset, int64_t head_capacity,
+                                       int32_t* overflow, void* status_ws, mfb200_stream_t stream) {
+    MFB_REQUIRE(k && v && k_strides && v_strides && k_bmp && k_idx && k_nz && k_head_base && v_bmp && v_idx && v_nz &&
+                    v_head_base && status_ws, "compress_prefill: null pointer");
+    MFB_REQUIRE(tokens >= 0 && tokens % 64 == 0, "compress_prefill: tokens=%lld must be a multiple of 64", static_cast<long long>(tokens));
+    MFB_REQUIRE(batch >= 0 && kv_heads >= 1 && static_cast<int64_t>(batch) * kv_heads <= 65535, "compress_prefill: batch*kv_heads out of range");
+    MFB_REQUIRE(prune_k_key >= 0 && prune_k_key <= kHeadDim && prune_k_value >= 0 && prune_k_value <= kHeadDim,
+                "compress_prefill: prune_k out of [0,128]");
+    MFB_REQUIRE(tile_offset >= 0 && tile_offset % 128 == 0 && bmp_stride >= tile_offset + tokens * 2 && idx_stride >= tile_offset + tokens * 2 + 1,
+                "compress_prefill: cache slab too small for tile_offset=%lld", static_cast<long long>(tile_offset));
+    MFB_REQUIRE(tokens / 64 <= 0x7fffffff, "compress_prefill: too many blocks");
+    for (int w = 0; w < 2; ++w) {
+        const int64_t* st = w ? v_strides : k_strides;
+        MFB_REQUIRE((reinterpret_cast<uintptr_t>(w ? v : k) & 7) == 0 && st[0] % 4 == 0 && st[1] % 4 == 0 && st[2] % 4 == 0 && st[2] >= kHeadDim,
+                    "compress_prefill: %s must be 8-byte aligned with strides that are multiples of 4 halves", w ? "v" : "k");
+    }
+    const int64_t units = static_cast<int64_t>(batch) * kv_heads, nblk = tokens / 64;
+    if (units == 0 || nblk == 0) return MFB200_OK;
+    auto s = static_cast<cudaStream_t>(stream);
+    MFB_CUDA(cudaMemsetAsync(status_ws, 0, static_cast<size_t>(2 * units * nblk) * sizeof(unsigned long long), s));
+    PrefillArgs a;
+    a.x[0] = static_cast<const __half*>(k);
+    a.x[1] = static_cast<const __half*>(v);
+    for (int w = 0; w < 2; ++w) {
+        const int64_t* st = w ? v_strides : k_strides;
+        a.stride_b[w] = st[0];
+        a.stride_h[w] = st[1];
+        a.stride_t[w] = st[2];
+    }
+    a.kv_heads = kv_heads;
+    a.prune_k[0] = prune_k_key;
+    a.prune_k[1] = prune_k_value;
+    a.bmp[0] = k_bmp;
+    a.bmp[1] = v_bmp;
+    a.idx[0] = k_idx;
+    a.idx[1] = v_idx;
+    a.nz[0] = static_cast<__half*>(k_nz);
+    a.nz[1] = static_cast<__half*>(v_nz);
+    a.head_base[0] = k_head_base;
+    a.head_base[1] = v_head_base;
+    a.bmp_stride = bmp_stride;
+    a.idx_stride = idx_stride;
+    a.tile_offset = tile_offset;
+    a.head_capacity = head_capacity;
+    a.overflow = overflow;
+    a.status = static_cast<unsigned long long*>(status_ws);
+    dim3 grid(static_cast<unsigned>(nblk), static_cast<unsigned>(units), 2);
+    compress_prefill_kernel<<<grid, kCompressThreads, 0, s>>>(a);
+    return launch_status("compress_prefill_kernel");
 }

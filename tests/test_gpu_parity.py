@@ -299,6 +299,72 @@ def test_cache_matches_whole_compression_and_reference_container():
     assert d.max() <= MAX_ABS and d.mean() <= MEAN_ABS
 
 
+def _check_prompt_streams(cache, kp, vp, L, ks, vs):
+    """cache streams == oracle compression of the pruned prompt rows [0, L) (bit-exact)."""
+    kc, _, vc, _, L2, _ = cache.as_reference_tuple()
+    assert L2 == L
+    b, hkv = kp.shape[:2]
+    kpr = O.prune_rows(kp[:, :, :L], ks).reshape(b * hkv, L, 128)
+    vpr = O.prune_rows(vp[:, :, :L], vs).reshape(b * hkv, L, 128)
+    for got, (rb, ra, rp) in ((kc, O.convert_key_batched(kpr)), (vc, O.convert_value_batched(vpr))):
+        assert np.array_equal(got[0].cpu().numpy(), rb)
+        assert np.array_equal(got[1].cpu().numpy(), ra)
+        assert all(np.array_equal(_bits(a.cpu().numpy()), _bits(r)) for a, r in zip(got[2], rp))
+        assert np.array_equal(got[3].cpu().numpy(), O.nz_offsets(ra))
+
+
+@pytest.mark.parametrize("b,hkv,T,ks,vs,layout", [
+    (2, 3, 256 * 3 + 40, 0.5, 0.7, "bhtd"),     # a few blocks, different K / V sparsity
+    (1, 2, 64 * 70 + 32, 0.7, 0.5, "bthd"),     # look-back across more than 32 predecessors; token-major source
+    (3, 2, 1024 + 32, 0.0, 0.9, "sliced"),      # no pruning for K; source = a slice of a longer buffer
+])
+def test_prefill_single_pass_bit_exact(b, hkv, T, ks, vs, layout):
+    """mfb200_compress_prefill (one launch, strided input, look-back offsets) vs the oracle's prune + convert."""
+    from mustafar_b200.attention import MustafarKVCache
+    kp, vp = _randn((b, hkv, T, 128), 21).numpy(), _randn((b, hkv, T, 128), 22).numpy()
+    kp[0, 0, 5] = 0.0          # an all-zero row (every tile bit 0 there)
+    kp[0, 1, 7, :64] = 0.25    # ties at the threshold: all kept
+    kt, vt = torch.from_numpy(kp).cuda(), torch.from_numpy(vp).cuda()
+    if layout == "bthd":       # [B, T, H, D] storage viewed as [B, H, T, D]
+        kt = kt.permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)
+        vt = vt.permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)
+        assert not kt.is_contiguous()
+    elif layout == "sliced":
+        kt = torch.cat([kt, torch.zeros_like(kt)], dim=2)[:, :, :T]
+        vt = torch.cat([vt, torch.zeros_like(vt)], dim=2)[:, :, :T]
+        assert not kt.is_contiguous()
+    cache = MustafarKVCache(b, hkv, 1, T + 300, ks, vs)
+    cache.prefill(kt, vt)
+    L = O.compressed_length(T)
+    assert cache.comp_len == L and cache.win_len == T - L
+    _check_prompt_streams(cache, kp, vp, L, ks, vs)
+    cache.check_overflow()
+
+
+def test_prefill_long_chain_and_append_offset():
+    """One unit with 1024 blocks (the look-back chain spans the whole grid), then a second compress call that
+    appends at a non-zero tile offset == compressing everything at once."""
+    from mustafar_b200.attention import MustafarKVCache
+    b, hkv, T = 1, 1, 64 * 1024 + 32
+    kp, vp = _randn((b, hkv, T, 128), 31).numpy(), _randn((b, hkv, T, 128), 32).numpy()
+    kt, vt = torch.from_numpy(kp).cuda(), torch.from_numpy(vp).cuda()
+    cache = MustafarKVCache(b, hkv, 1, T + 300, 0.5, 0.5)
+    cache.prefill(kt, vt)
+    L = O.compressed_length(T)
+    _check_prompt_streams(cache, kp, vp, L, 0.5, 0.5)
+    # two-stage: first 256 * 3 tokens, then the rest at tile offset 1536
+    c2 = MustafarKVCache(b, hkv, 1, T + 300, 0.5, 0.5)
+    L1 = 768
+    c2._compress_prompt(kt, vt, L1)
+    c2.comp_len = L1
+    c2._compress_prompt(kt[:, :, L1:], vt[:, :, L1:], L - L1)
+    c2.comp_len = L
+    for a, r in ((c2.k, cache.k), (c2.v, cache.v)):
+        assert torch.equal(a.bmp[:, : 2 * L], r.bmp[:, : 2 * L]) and torch.equal(a.idx[:, : 2 * L + 1], r.idx[:, : 2 * L + 1])
+        n = int(r.idx[0, 2 * L].item()) * 2
+        assert torch.equal(a.nz[:n].view(torch.int16), r.nz[:n].view(torch.int16))
+
+
 def test_slab_overflow_is_detected_not_corrupting():
     from mustafar_b200.attention import MustafarKVCache
     b, hkv = 1, 2

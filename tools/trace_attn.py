@@ -81,6 +81,19 @@ def main():
         print(f"  (V last - q staged) / blocks: p50 {np.median(per_blk):.2f} us/block")
         sm = np.bincount(t[:, 11].astype(int), minlength=148)
         print(f"  CTAs per SM: min {sm.min()} max {sm.max()}")
+        # balance: group the compressed CTAs by (own blocks, blocks of all compressed CTAs on the same SM)
+        ids = np.nonzero(live)[0][comp]
+        smid = tc[:, 11].astype(int)
+        sm_blocks = np.bincount(smid, weights=tc[:, 12], minlength=148)
+        sm_ctas = np.bincount(smid, minlength=148)
+        key = [(int(tc[i, 12]), int(sm_ctas[smid[i]]), int(sm_blocks[smid[i]])) for i in range(len(tc))]
+        for k in sorted(set(key)):
+            sel = np.array([kk == k for kk in key])
+            d = (tc[sel, 7] - t0) / 1e3
+            print(f"  own blocks {k[0]}, {k[1]} compressed CTAs / {k[2]} blocks on its SM: {sel.sum():3d} CTAs, V last p50 {np.median(d):6.2f} max {d.max():6.2f} us")
+        first_wave = ids < 148
+        if first_wave.any():
+            print(f"  ids 0..147 landed on {len(set(smid[first_wave]))} distinct SMs; ids 148..295 on {len(set(smid[(ids >= 148) & (ids < 296)]))}")
 
 
 if __name__ == "__main__":
