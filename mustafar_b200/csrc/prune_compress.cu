@@ -20,27 +20,45 @@ namespace mfb {
 constexpr int kPitch = kHeadDim + 2;  // halves; 65 words -> conflict-free column reads
 constexpr int kCompressThreads = 256;
 
-// k-th smallest of the 128 magnitudes held 4 per lane (15-bit integer keys), k in [1,128].
+// k-th smallest of the 128 magnitudes of a row, held 4 per lane as two registers of two packed 15-bit keys
+// (kx = v.x & 0x7fff7fff, ky = v.y & 0x7fff7fff), k in [1,128].
 // Greedy MSB-first construction of the largest T with count(key < T) < k  ==  the k-th smallest.
-__device__ __forceinline__ uint32_t warp_kth_smallest(const uint32_t (&m)[4], int k) {
-    uint32_t t = 0;
+// One round costs ~9 instructions: with c = cand - 1 replicated into both 16-bit fields, (0x8000 + c) - key stays
+// inside its field and has bit 15 set iff key < cand, so ONE subtraction compares two keys; a sign-replicating PRMT
+// turns the four flag bits into 0x00 / 0xFF bytes, IDP4A sums them (255 per hit), REDUX.SUM adds the lanes.
+// `u` carries threshold + this round's bias so that the bias costs no instruction of its own.
+// (A compare/select/add chain per key was 17 instructions per round and made the prune ALU-bound at 1.9 TB/s.)
+__device__ __forceinline__ uint32_t warp_kth_smallest(uint32_t kx, uint32_t ky, int k) {
+    constexpr uint32_t kRep = 0x10001u;
+    // Round `bit` tests cand = t | 2^bit.  u = 0x8000 + cand - 1 in both fields; accepting the bit moves the next
+    // round's u up by 2^(bit-1), rejecting it moves it down by 2^(bit-1) (fields never carry or borrow).
+    uint32_t u = 0x80008000u + ((1u << 14) - 1u) * kRep;
+    const uint32_t k255 = static_cast<uint32_t>(k) * 255u;
+    bool accept = false;
 #pragma unroll
     for (int bit = 14; bit >= 0; --bit) {
-        const uint32_t cand = t | (1u << bit);
-        uint32_t c = (m[0] < cand) + (m[1] < cand) + (m[2] < cand) + (m[3] < cand);
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c < static_cast<uint32_t>(k)) t = cand;
+        uint32_t flags;
+        asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(flags) : "r"(u - kx), "r"(u - ky));  // sign bytes of the 4 fields
+        const uint32_t c255 = __reduce_add_sync(0xffffffffu, __dp4a(flags, 0x01010101u, 0u));
+        accept = c255 < k255;  // fewer than k keys below cand: the k-th smallest is >= cand
+        if (bit > 0) {
+            const uint32_t delta = (1u << (bit - 1)) * kRep;
+            u += accept ? delta : 0u - delta;
+        }
     }
-    return t;
+    return (u & 0x7fffu) + (accept ? 1u : 0u);  // round 0: u = 0x8000 + t
 }
 
 // Applies  x * (|x| >= thr)  to 4 halves packed in a uint2; dropped entries keep their sign bit
 // (fp16 x * 0 = +-0), exactly what `key_states_flat * mask` produces.
 __device__ __forceinline__ uint2 prune4(uint2 v, int k) {
-    uint32_t m[4] = {v.x & 0x7fffu, (v.x >> 16) & 0x7fffu, v.y & 0x7fffu, (v.y >> 16) & 0x7fffu};
-    const uint32_t thr = warp_kth_smallest(m, k);
-    uint32_t keep_lo = (m[0] >= thr ? 0xffffu : 0x8000u) | (m[1] >= thr ? 0xffff0000u : 0x80000000u);
-    uint32_t keep_hi = (m[2] >= thr ? 0xffffu : 0x8000u) | (m[3] >= thr ? 0xffff0000u : 0x80000000u);
+    const uint32_t kx = v.x & 0x7fff7fffu, ky = v.y & 0x7fff7fffu;
+    const uint32_t thr = warp_kth_smallest(kx, ky, k);
+    // per field: key >= thr  <=>  bit 15 of (0x8000 + key - thr); widen the flag to a keep mask, the sign bit always stays
+    const uint32_t tb = thr * 0x10001u;
+    const uint32_t gx = ((kx | 0x80008000u) - tb) & 0x80008000u, gy = ((ky | 0x80008000u) - tb) & 0x80008000u;
+    const uint32_t keep_lo = (gx - (gx >> 15)) | 0x80008000u;  // 0x8000 -> 0x7fff per field, 0 -> 0; then | sign bits
+    const uint32_t keep_hi = (gy - (gy >> 15)) | 0x80008000u;
     return make_uint2(v.x & keep_lo, v.y & keep_hi);
 }
 
