@@ -61,12 +61,6 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-    return v;
-}
-
 __device__ __forceinline__ float h2f_bits(uint32_t bits16) {
     return __half2float(__ushort_as_half(static_cast<unsigned short>(bits16)));
 }
@@ -96,9 +90,6 @@ __device__ __forceinline__ void mbar_inval(uint64_t* bar) {
 }
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)

@@ -392,6 +392,42 @@ def test_repeated_launches_are_stable_and_correct(b, hkv, groups, T, sparsity):
     assert d.max() <= MAX_ABS and d.mean() <= MEAN_ABS, (d.max(), d.mean())
 
 
+def test_decode_launches_replay_in_a_cuda_graph():
+    """The fused launch is graph-capturable (single kernel, PDL attribute, self-resetting tickets): capture three
+    launches on different caches, replay twice, compare with the eager launches."""
+    import ctypes as C
+    from mustafar_b200 import _lib
+    lib = _lib.load()
+    cases = [_attention_case(2, 4, g, 1500, 0.5, seed=70 + g) for g in (1, 4)] + [_attention_case(1, 8, 1, 4200, 0.7, seed=77)]
+    params, outs, eager = [], [], []
+    for cache, q, kp, vp, L in cases:
+        qd = q.cuda()
+        eager.append(cache.attend(qd).clone())
+        o = torch.zeros_like(qd)
+        p = cache.make_params(qd.view(cache.batch, -1, 128), o)
+        p.flags |= _lib.F_PDL
+        params.append((p, qd))
+        outs.append(o)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for p, _ in params:  # warm-up on the capture stream (first-call attribute setup must not happen under capture)
+            _lib.check(lib.mfb200_sparse_decode_attention(C.byref(p), side.cuda_stream), "warm-up")
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        for p, _ in params:
+            _lib.check(lib.mfb200_sparse_decode_attention(C.byref(p), torch.cuda.current_stream().cuda_stream), "capture")
+    for _ in range(2):
+        for o in outs:
+            o.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        for o, e in zip(outs, eager):
+            assert torch.equal(o.view_as(e), e)
+
+
 def test_flat_partition_mode():
     """Mid-size launches use the flat work partition (all blocks of all units divided evenly over the resident
     CTA slots; CTAs cross unit boundaries and process several segments).  Forced here on small shapes through the
