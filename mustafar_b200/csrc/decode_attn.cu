@@ -34,7 +34,7 @@ namespace mfb {
 #define MFB_G1_CTAS 3  // resident CTAs per SM the G=1 kernel is compiled for (64 registers, no spills; +3..6 % at batch 1)
 #endif
 constexpr int kTileWarps = 4;                 // per role
-constexpr int kWarpK0 = 0, kWarpV0 = 4, kWarpSoftmax = 8, kWarpProducer = 9;
+constexpr int kWarpV0 = 4, kWarpSoftmax = 8, kWarpProducer = 9;  // warps 0-3: K role
 constexpr int kAttnWarps = 10;
 constexpr int kAttnThreads = kAttnWarps * 32;  // 320
 constexpr int kWinWarps = 8;                   // warps used by the dense-window path
@@ -60,19 +60,30 @@ struct DecodeArgs {
 };
 
 // barrier indices inside the bars[] array
+// mbarriers (shared memory) carry the hand-offs whose waiter normally finds them already complete, and the TMA
+// transaction counts; the many -> one hand-offs whose single waiter sleeps most of the time (K warps -> softmax,
+// V warps -> softmax, tile warps -> producer) use hardware named barriers instead: a warp parked in bar.sync issues
+// nothing, whereas an mbarrier waiter is woken by every event on the CTA's mbarriers and re-polls (measured: 17 %
+// of all issued instructions of a large MHA launch were such polls).
 struct Bars {
     enum : int {
-        kFullK = 0,                  // [depth] producer -> K warps
-        kEmptyK = kMaxDepth,         // [depth] K warps -> producer      (count 4)
-        kFullV = 2 * kMaxDepth,      // [depth]
-        kEmptyV = 3 * kMaxDepth,     // [depth]                          (count 4)
-        kScFull = 4 * kMaxDepth,     // [2] K warps -> softmax           (count 4)
-        kScEmpty = kScFull + 2,      // [2] softmax -> K warps           (count 1)
+        kFullK = 0,                  // [depth] producer (TMA tx) -> K warps
+        kFullV = kMaxDepth,          // [depth] producer (TMA tx) -> V warps
+        kScEmpty = 2 * kMaxDepth,    // [2] softmax -> K warps           (count 1)
         kPFull = kScEmpty + 2,       // [2] softmax -> V warps           (count 1)
-        kPEmpty = kPFull + 2,        // [2] V warps -> softmax           (count 4)
-        kCount = kPEmpty + 2
+        kCount = kPFull + 2
     };
 };
+// named barrier ids (0 is __syncthreads); every one joins 4 arriving tile warps and 1 waiting warp
+struct NamedBars {
+    enum : int {
+        kScFull = 1,   // [2] K warps arrive, softmax warp syncs
+        kPEmpty = 3,   // [2] V warps arrive, softmax warp syncs
+        kEmptyK = 5,   // [depth <= 4] K warps arrive, producer warp syncs
+        kEmptyV = 9,   // [depth <= 4] V warps arrive, producer warp syncs
+    };
+};
+constexpr int kHandoffThreads = (kTileWarps + 1) * 32;
 
 struct SmemMap {
     uint32_t slots_k, slots_v, bars, rec, qs, spart, ps, corr, stat, segk, segv, dense, total;
@@ -135,6 +146,12 @@ __device__ __forceinline__ void trace_at(int k) {
 #define MFB_TRACE_VAL(k, v) ((void)0)
 #endif
 
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {  // whole warp; orders the warp's earlier accesses
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -348,15 +365,11 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             }
             for (int s = 0; s < kMaxDepth; ++s) {
                 mbar_init(&bars[Bars::kFullK + s], 1);
-                mbar_init(&bars[Bars::kEmptyK + s], kTileWarps);
                 mbar_init(&bars[Bars::kFullV + s], 1);
-                mbar_init(&bars[Bars::kEmptyV + s], kTileWarps);
             }
             for (int s = 0; s < 2; ++s) {
-                mbar_init(&bars[Bars::kScFull + s], kTileWarps);
                 mbar_init(&bars[Bars::kScEmpty + s], 1);
                 mbar_init(&bars[Bars::kPFull + s], 1);
-                mbar_init(&bars[Bars::kPEmpty + s], kTileWarps);
             }
             fence_mbar_init();
         }
@@ -367,31 +380,30 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     const uint8_t* v_nz = static_cast<const uint8_t*>(p.v_nz) + p.v_nz_off[unit] * 16;
     const uint64_t* k_bmp = p.k_bmp + static_cast<int64_t>(unit) * p.bmp_stride + static_cast<int64_t>(blk0) * 128;
     const uint64_t* v_bmp = p.v_bmp + static_cast<int64_t>(unit) * p.bmp_stride + static_cast<int64_t>(blk0) * 128;
-    // producer state: block n -> ring slot ps_slot, parity ps_par of the slot's EMPTY barrier
+    // producer state: block pn -> ring slot ps_slot.  The whole producer warp runs this (bar.sync is warp-wide);
+    // lane 0 issues the copies.  A slot's first use needs no wait; later uses wait for its 4 consumer warps.
     int pn = 0, ps_slot = 0;
-    uint32_t ps_par = 1;  // fresh barrier: the "previous" phase counts as complete
-    auto produce_until = [&](int limit) {  // producer lane only
+    auto produce_until = [&](int limit) {
         for (; pn < limit; ++pn, ++ps_slot) {
-            if (ps_slot == D) {
-                ps_slot = 0;
-                ps_par ^= 1;
-            }
+            if (ps_slot == D) ps_slot = 0;
 #pragma unroll
             for (int is_v = 0; is_v < 2; ++is_v) {
-                uint64_t* full = &bars[(is_v ? Bars::kFullV : Bars::kFullK) + ps_slot];
-                mbar_wait_relaxed(&bars[(is_v ? Bars::kEmptyV : Bars::kEmptyK) + ps_slot], ps_par);  // producer: sleep between polls
-                const uint32_t* seg = is_v ? segv : segk;
-                const uint32_t off0 = seg[pn * 4], bytes = (seg[pn * 4 + 4] - off0) * 4u;
-                const bool fits = bytes <= static_cast<uint32_t>(a.slot_nz_bytes);
-                uint8_t* dst = smem + (is_v ? sm.slots_v : sm.slots_k) + ps_slot * slot_bytes;
-                mbar_expect_tx(full, 1024u + ((fits && bytes) ? bytes : 0u));
-                bulk_g2s(dst, (is_v ? v_bmp : k_bmp) + pn * 128, 1024u, full);
-                if (fits && bytes) bulk_g2s(dst + 1024, (is_v ? v_nz : k_nz) + static_cast<uint64_t>(off0) * 4u, bytes, full);
+                if (pn >= D) bar_sync((is_v ? NamedBars::kEmptyV : NamedBars::kEmptyK) + ps_slot, kHandoffThreads);
+                if (lane == 0) {
+                    uint64_t* full = &bars[(is_v ? Bars::kFullV : Bars::kFullK) + ps_slot];
+                    const uint32_t* seg = is_v ? segv : segk;
+                    const uint32_t off0 = seg[pn * 4], bytes = (seg[pn * 4 + 4] - off0) * 4u;
+                    const bool fits = bytes <= static_cast<uint32_t>(a.slot_nz_bytes);
+                    uint8_t* dst = smem + (is_v ? sm.slots_v : sm.slots_k) + ps_slot * slot_bytes;
+                    mbar_expect_tx(full, 1024u + ((fits && bytes) ? bytes : 0u));
+                    bulk_g2s(dst, (is_v ? v_bmp : k_bmp) + pn * 128, 1024u, full);
+                    if (fits && bytes) bulk_g2s(dst + 1024, (is_v ? v_nz : k_nz) + static_cast<uint64_t>(off0) * 4u, bytes, full);
+                }
+                __syncwarp();
             }
         }
     };
-    const bool is_producer = (warp == kWarpProducer) && (lane == 0);
-    if (is_producer) produce_until(nb < D ? nb : D);  // first ring-full: never blocks
+    if (warp == kWarpProducer) produce_until(nb < D ? nb : D);  // first ring-full: never blocks
     if (early_kv) pdl_wait_prior_grids();
     if (tid == 0) MFB_TRACE_AT(2);
     {
@@ -413,7 +425,13 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
 
     if (warp == kWarpProducer) {
         // =========================== producer ===========================
-        if (is_producer) produce_until(nb);
+        produce_until(nb);
+        // the arrivals of the last ring-full have no refill that would consume them: drain, so that every named
+        // barrier is back in its initial state when the split ends (a flat-mode CTA runs another segment)
+        for (int j = nb > D ? nb - D : 0; j < nb; ++j) {
+            bar_sync(NamedBars::kEmptyK + j % D, kHandoffThreads);
+            bar_sync(NamedBars::kEmptyV + j % D, kHandoffThreads);
+        }
     } else if (warp == kWarpSoftmax) {
         // =========================== online softmax ===========================
         // Head-parallel lane mapping: 32/G lanes per query head, each lane owns 2G consecutive tokens of the
@@ -425,11 +443,10 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         float m_run = -INFINITY, l_run = 0.f;
         for (int n = 0; n < nb; ++n) {
             const int buf = n & 1;
-            const uint32_t par = (n >> 1) & 1;
             float mk[TPL];
 #pragma unroll
             for (int i = 0; i < TPL; ++i) mk[i] = mask ? __half2float(mask[(blk0 + n) * kBlockTokens + t0 + i]) : 0.f;
-            mbar_wait(&bars[Bars::kScFull + buf], par);
+            bar_sync(NamedBars::kScFull + buf, kHandoffThreads);  // the 4 K warps' partial scores of block n
             float sc[TPL];
 #pragma unroll
             for (int i = 0; i < TPL; ++i) sc[i] = 0.f;
@@ -466,7 +483,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             for (int o = LPH / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             l_run = l_run * cr + sum;
             m_run = m_new;
-            mbar_wait(&bars[Bars::kPEmpty + buf], par ^ 1);
+            if (n >= 2) bar_sync(NamedBars::kPEmpty + buf, kHandoffThreads);  // V warps are done with p of block n-2
             if constexpr (G >= 4) {  // tensor-core variant: p as [g][64 tokens] (A-fragment pairs are along tokens)
                 __half* pb = ps + (buf * G + hg) * kTcRowPitch + t0;
 #pragma unroll
@@ -484,6 +501,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             stat[hg] = m_run;
             stat[8 + hg] = l_run;
         }
+        for (int j = nb > 2 ? nb - 2 : 0; j < nb; ++j) bar_sync(NamedBars::kPEmpty + (j & 1), kHandoffThreads);  // drain
     } else {
         // =========================== K / V tile warps ===========================
         const bool is_v = warp >= kWarpV0;
@@ -494,7 +512,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         const uint32_t* seg = is_v ? segv : segk;
         const uint8_t* nz_g = is_v ? v_nz : k_nz;
         const uint32_t slots_off = is_v ? sm.slots_v : sm.slots_k;
-        const int full0 = is_v ? Bars::kFullV : Bars::kFullK, empty0 = is_v ? Bars::kEmptyV : Bars::kEmptyK;
+        const int full0 = is_v ? Bars::kFullV : Bars::kFullK, empty0 = is_v ? NamedBars::kEmptyV : NamedBars::kEmptyK;
         // tensor-core variant state: q A-fragments (K warps, constant) and the o accumulator fragments (V warps)
         uint32_t qfrag[2][2] = {{0u, 0u}, {0u, 0u}};
         float oacc[8][4];
@@ -536,7 +554,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                 if (fits) decode_to_dense32<true>(my_rec, lc, gblk, dense_addr);
                 else decode_to_dense32<false>(my_rec, lc, gblk, dense_addr);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[empty0 + s]);  // ring slot no longer needed
+                bar_arrive(empty0 + s, kHandoffThreads);  // ring slot no longer needed
                 if (!is_v) {
                     // scores[g][token] += q[g][channels 32w..32w+31] . K : A = q rows (constant), B = dense (channel x token)
                     float acc[8][4];
@@ -550,7 +568,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                         for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<float2*>(sp + 8 * nt) = make_float2(acc[nt][0], acc[nt][1]);
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars[Bars::kScFull + buf]);
+                    bar_arrive(NamedBars::kScFull + buf, kHandoffThreads);
                 } else {
                     // out[g][channel] += p[g][tokens] . V : A = p rows of this block, B = dense (token x channel)
                     mbar_wait(&bars[Bars::kPFull + buf], par2);
@@ -565,7 +583,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                         c = corr[buf * 8 + gid];
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars[Bars::kPEmpty + buf]);
+                    bar_arrive(NamedBars::kPEmpty + buf, kHandoffThreads);
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) {
                         oacc[nt][0] *= c;
@@ -580,13 +598,13 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                 for (int g = 0; g < G; ++g) sc[g][0] = sc[g][1] = 0.f;
                 tiles32<G>(fits, my_rec, lc, gblk, qs + (32 * w) * G, sc);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[empty0 + s]);
+                bar_arrive(empty0 + s, kHandoffThreads);
                 mbar_wait(&bars[Bars::kScEmpty + buf], par2 ^ 1);
                 float* sp = spart + ((buf * kTileWarps + w) * G) * 64;
 #pragma unroll
                 for (int g = 0; g < G; ++g) *reinterpret_cast<float2*>(sp + g * 64 + 2 * lane) = make_float2(sc[g][0], sc[g][1]);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[Bars::kScFull + buf]);
+                bar_arrive(NamedBars::kScFull + buf, kHandoffThreads);
                 if (tid == 0 && n == 0) MFB_TRACE_AT(4);
                 if (tid == 0 && n == nb - 1) MFB_TRACE_AT(5);
             } else {
@@ -600,10 +618,8 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                 }
                 tiles32<G>(fits, my_rec, lc, gblk, ps + (buf * 64 + 32 * (w & 1)) * G, o_acc);
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&bars[empty0 + s]);
-                    mbar_arrive(&bars[Bars::kPEmpty + buf]);
-                }
+                bar_arrive(empty0 + s, kHandoffThreads);
+                bar_arrive(NamedBars::kPEmpty + buf, kHandoffThreads);
                 if (tid == kWarpV0 * 32 && n == 0) MFB_TRACE_AT(6);
                 if (tid == kWarpV0 * 32 && n == nb - 1) MFB_TRACE_AT(7);
             }

@@ -10,7 +10,7 @@ if [ "$WHAT" = launches ]; then
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
 else
   timeout 200 python tools/prof_attn.py $WHAT 1 > gpurun_out/${TAG}_prof_plain_$WHAT.log 2>&1 || exit 1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:sparse_decode_attn -s 4 -c 1 -f -o gpurun_out/${TAG}_attn_$WHAT \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:sparse_decode_attn -s $([ "$WHAT" = cfg1 ] && echo 4 || echo 3) -c 1 -f -o gpurun_out/${TAG}_attn_$WHAT \
       python tools/prof_attn.py $WHAT 1 > gpurun_out/${TAG}_ncu_$WHAT.log 2>&1
 fi
 ls -la gpurun_out/${TAG}_* | tail -5
