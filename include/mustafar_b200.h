@@ -199,7 +199,10 @@ typedef struct mfb200_decode_params {
  * Decomposition (chosen inside the launch, same rule): small launches cut every unit into the same number of
  * compressed splits so that all CTAs are resident at once; large MHA launches (G <= 2, >= 24 blocks per resident
  * CTA slot) divide all units*blocks evenly over 1x or 2x the resident CTA slots, CTAs may cross unit boundaries.
- * Workspace layout: [counters: units*4 bytes, rounded to 256][partials fp32]. */
+ * Workspace layout: [per-unit launch epochs][per-unit tickets] (units*4 bytes each, rounded to 256; together
+ * counter_bytes) followed by the partials as 8-byte {fp32, tag} entries.
+ * The WHOLE workspace must be zero before the first launch on it (and again if batch / kv_heads / groups change);
+ * launches keep it consistent afterwards (tags only grow), so it is graph-replayable. */
 int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count,
                        size_t* workspace_bytes, size_t* counter_bytes);
 int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb200_stream_t stream);

@@ -43,7 +43,7 @@ constexpr int kChunk = 16;                     // tiles per operand-register chu
 constexpr int kMaxDepth = 4;
 constexpr int kMaxBlocksPerSplit = 128;
 constexpr int kWinTokensPerSplit = 64;
-constexpr int kPartStride = 132;  // floats per (split, head): o[128], m, l, pad
+constexpr int kPartStride = 132;  // {fp32 value, tag} entries per (split, head): o[128], m, l, pad
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct DecodeArgs {
@@ -55,6 +55,7 @@ struct DecodeArgs {
     int flat_q;     //   B / n   -> CTA c owns global blocks [c*q + min(c, r), ...) : q + 1 blocks if c < r, else q
     int flat_r;     //   B % n
     int max_split;  // partial slots per unit in the workspace (>= every unit's segment count + n_wsplit)
+    int flagged;    // split-merge protocol: 1 = flagged partials + designated merger, 0 = ticket (see publish_or_merge)
     int slot_nz_bytes;  // capacity of a slot's nonzero area (multiple of 1024)
     int depth;          // ring depth per stream (K and V each), 2..4
 };
@@ -108,8 +109,8 @@ __host__ __device__ inline SmemMap smem_map(int G, int slot_nz_bytes, int depth)
     o += 2 * (G >= 4 ? kTcRowPitch : 64) * G * 2;
     m.corr = o;  // float [2][8]
     o += 2 * 8 * 4;
-    m.stat = o;  // float m[8], l[8]
-    o += 2 * 8 * 4;
+    m.stat = o;  // float m[8], l[8]; uint32 tag
+    o += 2 * 8 * 4 + 16;
     m.segk = o;
     o += (kMaxBlocksPerSplit * 4 + 4) * 4;
     m.segv = o;
@@ -182,74 +183,97 @@ __host__ __device__ inline int unit_csplits(const DecodeArgs& a, int unit) {
     return static_cast<int>(flat_owner(a, (unit + 1) * nblk - 1) - flat_owner(a, unit * nblk)) + 1;
 }
 
-// Writes this split's partial (o[G][128] from smem `ored`, m, l) into slot `split` of the unit and lets the last
-// of the unit's `n_split` contributors merge.  All threads of the CTA must call it.
-template <int G>
-__device__ __forceinline__ void write_partial_and_merge(const DecodeArgs& a, int unit, int split, int n_split,
-                                                        const float* ored, const float* m, const float* l, float* scratch) {
+// ---- split merge ---------------------------------------------------------------------------------------------
+// Every contributor of a unit writes its fp32 partial (o[G][128], m, l) into its slot as 8-byte entries
+// {value, tag}; tag = the unit's launch epoch + 1 (read from the workspace after the PDL wait).  Two protocols:
+//  * ticket (long launches): stores -> CTA barrier -> acq_rel atomic ticket; the LAST ARRIVAL merges.  Merges are
+//    spread over the launch and nobody ever waits, at the price of two dependent L2 round trips (release, ticket)
+//    before the merge can start.
+//  * flagged (short launches, where that tail is ~8 % of the launch): contributors store and leave at once - no
+//    fence, no ticket, no barrier.  The owner of the unit's LAST slot (the last window chunk, or the last compressed
+//    split when there is no window) merges: its own partial stays in shared memory, the others are folded straight
+//    from L2, an entry counting only when its tag matches; a pass that met a stale entry is repeated after a short
+//    sleep.  The merger has the highest CTA index of its unit, so everything it waits for was dispatched before
+//    it: the wait cannot deadlock.
+__device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const void* p) {
+    uint32_t r;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+// workspace: [epochs: units u32 | 256-byte rounded][tickets: units s32 | 256-byte rounded][partials]
+__host__ __device__ inline size_t ws_counter_bytes(size_t units) { return (units * 4 + 255) & ~static_cast<size_t>(255); }
+__device__ __forceinline__ uint32_t* epoch_ptr(const mfb200_decode_params& p, int unit) {
+    return static_cast<uint32_t*>(p.workspace) + unit;
+}
+__device__ __forceinline__ int* ticket_ptr(const mfb200_decode_params& p, int unit) {
+    return reinterpret_cast<int*>(static_cast<uint8_t*>(p.workspace) + ws_counter_bytes(p.batch * p.kv_heads)) + unit;
+}
+__device__ __forceinline__ uint2* partial_ptr(const DecodeArgs& a, int G, int unit, int slot) {
+    uint2* parts = reinterpret_cast<uint2*>(static_cast<uint8_t*>(a.p.workspace) + 2 * ws_counter_bytes(a.p.batch * a.p.kv_heads));
+    return parts + (static_cast<int64_t>(unit) * a.max_split + slot) * G * kPartStride;
+}
+
+// Folds the unit's n_split partials and writes the output rows.  kOwn: slot `split` is taken from shared memory
+// (ored, m, l) and the others are accepted only with a matching tag (flagged protocol); otherwise every slot is read
+// from the workspace and trusted (ticket protocol: the acquire already ordered them).
+// One global round trip per pass: each warp folds a strided subset of one head's partials with all its loads in
+// flight (128-bit, L2), the per-warp results are combined through `scratch`.
+template <int G, bool kOwn>
+__device__ __forceinline__ void merge_unit(const DecodeArgs& a, int unit, int split, int n_split, uint32_t tag,
+                                           const float* ored, const float* m, const float* l, float* scratch) {
     const mfb200_decode_params& p = a.p;
-    const int tid = threadIdx.x;
-    const int units = p.batch * p.kv_heads;
-    int* counters = static_cast<int*>(p.workspace);
-    float* parts = reinterpret_cast<float*>(static_cast<uint8_t*>(p.workspace) + ((units * 4 + 255) & ~255));
-    float* mine = parts + (static_cast<int64_t>(unit) * a.max_split + split) * G * kPartStride;
-    for (int i = tid; i < G * 128; i += kAttnThreads) mine[(i >> 7) * kPartStride + (i & 127)] = ored[i];
-    if (tid < G) {
-        mine[tid * kPartStride + 128] = m[tid];
-        mine[tid * kPartStride + 129] = l[tid];
-    }
-    __shared__ int s_last;
-    // Release/acquire through the ticket: the CTA's partial stores happen-before thread 0's release (bar.sync), and
-    // thread 0's acquire happens-before the merge loads of the whole CTA (bar.sync) - no full fences needed.
-    __syncthreads();
-    if (tid == 0) {
-        int ticket;
-        asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(ticket) : "l"(&counters[unit]) : "memory");
-        s_last = (ticket == n_split - 1);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        MFB_TRACE_AT(9);
-        MFB_TRACE_VAL(13, static_cast<unsigned long long>(s_last));
-    }
-    if (!s_last) return;
-    // ---- merge (last contributor of the unit) -------------------------------------------------------------
-    // The merge sits on the launch's critical path (everyone else has already left), so it is organised for
-    // ONE global round trip: each warp folds a strided subset of the partials of one query head with all its
-    // loads in flight (128-bit, L2), then the per-warp results are combined through shared memory.
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int kWpg = (G <= 2 ? kAttnWarps : 8) / G;  // warps per query head: 10, 5, 2, 1
-    // `scratch`: kAttnWarps * kPartStride floats of dynamic shared memory that is dead by now (may alias `ored`,
-    // which was consumed before the barriers above).  Per warp: o[128], m, den.
-    float (*s_red)[kPartStride] = reinterpret_cast<float (*)[kPartStride]>(scratch);
-    const float* up = parts + static_cast<int64_t>(unit) * a.max_split * G * kPartStride;
-    const int warp = tid >> 5, lane = tid & 31;
-    if (warp < kWpg * G) {
-        const int g = warp % G;
-        float m_run = -INFINITY, den = 0.f;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float (*s_red)[kPartStride] = reinterpret_cast<float (*)[kPartStride]>(scratch);  // per warp: o[128], m, den
+    const uint2* up = partial_ptr(a, G, unit, 0);
+    for (uint32_t backoff = 128;; backoff = backoff < 1024 ? 2 * backoff : 1024) {
+        bool ok = true;
+        if (warp < kWpg * G) {
+            const int g = warp % G;
+            float m_run = -INFINITY, den = 0.f;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-        for (int s = warp / G; s < n_split; s += kWpg) {
-            const float* ps = up + (s * G + g) * kPartStride;
-            const float ms = __ldcg(ps + 128), ls = __ldcg(ps + 129);
-            const float4 o = __ldcg(reinterpret_cast<const float4*>(ps) + lane);
-            const float mn = fmaxf(m_run, ms);
-            // a partial with no visible token has m = -inf, l = 0, o = 0: weight it 0 (and avoid inf - inf)
-            const float so = (m_run == -INFINITY) ? 0.f : exp2f((m_run - mn) * kLog2e);
-            const float w = (ms == -INFINITY) ? 0.f : exp2f((ms - mn) * kLog2e);
-            den = den * so + ls * w;
-            acc.x = acc.x * so + o.x * w;
-            acc.y = acc.y * so + o.y * w;
-            acc.z = acc.z * so + o.z * w;
-            acc.w = acc.w * so + o.w * w;
-            m_run = mn;
+            for (int s = warp / G; s < n_split; s += kWpg) {
+                float ms, ls;
+                float4 o;
+                if (kOwn && s == split) {
+                    ms = m[g];
+                    ls = l[g];
+                    o = reinterpret_cast<const float4*>(ored + g * 128)[lane];
+                } else {
+                    const uint2* ps = up + (s * G + g) * kPartStride;
+                    const uint4 e0 = ld_relaxed_v4(ps + 4 * lane), e1 = ld_relaxed_v4(ps + 4 * lane + 2);
+                    const uint4 ml = ld_relaxed_v4(ps + 128);  // {m, tag, l, tag}
+                    if (kOwn) ok = ok && e0.y == tag && e0.w == tag && e1.y == tag && e1.w == tag && ml.y == tag && ml.w == tag;
+                    ms = __uint_as_float(ml.x);
+                    ls = __uint_as_float(ml.z);
+                    o = make_float4(__uint_as_float(e0.x), __uint_as_float(e0.z), __uint_as_float(e1.x), __uint_as_float(e1.z));
+                }
+                const float mn = fmaxf(m_run, ms);
+                // a partial with no visible token has m = -inf, l = 0, o = 0: weight it 0 (and avoid inf - inf)
+                const float so = (m_run == -INFINITY) ? 0.f : exp2f((m_run - mn) * kLog2e);
+                const float w = (ms == -INFINITY) ? 0.f : exp2f((ms - mn) * kLog2e);
+                den = den * so + ls * w;
+                acc.x = acc.x * so + o.x * w;
+                acc.y = acc.y * so + o.y * w;
+                acc.z = acc.z * so + o.z * w;
+                acc.w = acc.w * so + o.w * w;
+                m_run = mn;
+            }
+            reinterpret_cast<float4*>(s_red[warp])[lane] = acc;
+            if (lane == 0) {
+                s_red[warp][128] = m_run;
+                s_red[warp][129] = den;
+            }
         }
-        reinterpret_cast<float4*>(s_red[warp])[lane] = acc;
-        if (lane == 0) {
-            s_red[warp][128] = m_run;
-            s_red[warp][129] = den;
-        }
+        if (__syncthreads_and(ok)) break;  // also publishes s_red
+        __nanosleep(backoff);              // some contributor has not landed yet (stale tags): look again
     }
-    __syncthreads();
     for (int i = tid; i < G * 128; i += kAttnThreads) {
         const int g = i >> 7, c = i & 127;
         float mx = -INFINITY;
@@ -266,7 +290,54 @@ __device__ __forceinline__ void write_partial_and_merge(const DecodeArgs& a, int
         const int64_t qh = static_cast<int64_t>(unit) * G + g;  // = b*Hq + h*G + g
         static_cast<__half*>(p.out)[qh * kHeadDim + c] = __float2half_rn(num / den);
     }
-    if (tid == 0) counters[unit] = 0;  // ready for the next launch / graph replay
+    if (tid == 0) *epoch_ptr(p, unit) = tag;  // the next launch (stream-ordered / after its PDL wait) tags with tag + 1
+}
+
+// Publishes this split's partial (slot `split` of the unit) and merges the unit if it is this CTA's turn.
+// ored [G][128], m [G], l [G] live in shared memory.  All threads of the CTA call it.
+// `scratch`: kAttnWarps * kPartStride floats of dead dynamic shared memory, must not overlap ored / m / l.
+template <int G, bool FLAGGED>
+__device__ __forceinline__ void publish_or_merge(const DecodeArgs& a, int unit, int split, int n_split, uint32_t tag,
+                                                 const float* ored, const float* m, const float* l, float* scratch) {
+    const int tid = threadIdx.x;
+    if (FLAGGED && split == n_split - 1) {
+        if (tid == 0) {
+            MFB_TRACE_AT(9);
+            MFB_TRACE_VAL(13, 1ull);
+        }
+        merge_unit<G, true>(a, unit, split, n_split, tag, ored, m, l, scratch);
+        return;
+    }
+    uint2* mine = partial_ptr(a, G, unit, split);
+    for (int i = tid; i < G * 128; i += kAttnThreads)
+        mine[(i >> 7) * kPartStride + (i & 127)] = make_uint2(__float_as_uint(ored[i]), tag);
+    if (tid < G) {
+        mine[tid * kPartStride + 128] = make_uint2(__float_as_uint(m[tid]), tag);
+        mine[tid * kPartStride + 129] = make_uint2(__float_as_uint(l[tid]), tag);
+    }
+    int last = 0;
+    if constexpr (!FLAGGED) {
+        // Release/acquire through the ticket: the CTA's partial stores happen-before thread 0's release (bar.sync),
+        // and thread 0's acquire happens-before the merge loads of the whole CTA (bar.sync) - no full fences needed.
+        __shared__ int s_last;
+        __syncthreads();
+        if (tid == 0) {
+            int ticket;
+            asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(ticket) : "l"(ticket_ptr(a.p, unit)) : "memory");
+            s_last = (ticket == n_split - 1);
+        }
+        __syncthreads();
+        last = s_last;
+    }
+    if (tid == 0) {
+        MFB_TRACE_AT(9);
+        MFB_TRACE_VAL(13, static_cast<unsigned long long>(last));
+    }
+    if constexpr (!FLAGGED) {
+        if (!last) return;
+        merge_unit<G, false>(a, unit, split, n_split, tag, ored, m, l, scratch);
+        if (tid == 0) *ticket_ptr(a.p, unit) = 0;  // ready for the next launch / graph replay
+    }
 }
 
 // One chunk of 16 tiles.  `oper` = the per-tile fp16 FMA operands [16][G] in shared memory (q for K
@@ -321,7 +392,7 @@ __device__ __forceinline__ void tiles32(bool nz_shared, const uint2* rec, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int G>
+template <int G, bool FLAGGED>
 __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* smem, int unit, int split, int n_split,
                                                  int blk0, int blk1, bool again) {
     const mfb200_decode_params& p = a.p;
@@ -405,7 +476,10 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     };
     if (warp == kWarpProducer) produce_until(nb < D ? nb : D);  // first ring-full: never blocks
     if (early_kv) pdl_wait_prior_grids();
-    if (tid == 0) MFB_TRACE_AT(2);
+    if (tid == 0) {
+        MFB_TRACE_AT(2);
+        reinterpret_cast<uint32_t*>(stat)[16] = ld_relaxed_u32(epoch_ptr(p, unit)) + 1u;  // this launch's partial tag
+    }
     {
         const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
         for (int i = tid; i < G * kHeadDim; i += kAttnThreads) qs[(i & 127) * G + (i >> 7)] = q[i];
@@ -662,7 +736,8 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         ored[i] = red[((2 * hf) * G + g) * 64 + e] + red[((2 * hf + 1) * G + g) * 64 + e];
     }
     __syncthreads();
-    write_partial_and_merge<G>(a, unit, split, n_split, ored, stat, stat + 8, reinterpret_cast<float*>(smem));
+    publish_or_merge<G, FLAGGED>(a, unit, split, n_split, reinterpret_cast<const uint32_t*>(stat)[16], ored, stat, stat + 8,
+                        reinterpret_cast<float*>(smem + sm.slots_v));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -695,13 +770,13 @@ __host__ __device__ inline WinSmem win_smem_map(int G) {
     o += kWinWarps * G * 128 * 4;
     m.ored = o;  // float [G][128]
     o += G * 128 * 4;
-    m.ml = o;  // float m[8], l[8]
-    o += 64;
+    m.ml = o;  // float m[8], l[8]; uint32 tag
+    o += 64 + 16;
     m.total = o;
     return m;
 }
 
-template <int G>
+template <int G, bool FLAGGED>
 __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem, int unit, int split, int n_split, int wchunk) {
     const mfb200_decode_params& p = a.p;
     const WinSmem sm = win_smem_map(G);
@@ -725,6 +800,7 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
     pdl_launch_dependents();
     pdl_wait_prior_grids();  // the window is written by the previous step's launch
     if (tid == 0) {
+        reinterpret_cast<uint32_t*>(ml)[16] = ld_relaxed_u32(epoch_ptr(p, unit)) + 1u;  // this launch's partial tag
         mbar_init(bar, 1);
         fence_mbar_init();
         const __half* kw = static_cast<const __half*>(p.k_win) + static_cast<int64_t>(unit) * p.win_stride + static_cast<int64_t>(t0) * kHeadDim;
@@ -857,11 +933,14 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
         ored[i] = s;
     }
     __syncthreads();
-    write_partial_and_merge<G>(a, unit, split, n_split, ored, ml, ml + 8, reinterpret_cast<float*>(smem));
+    publish_or_merge<G, FLAGGED>(a, unit, split, n_split, reinterpret_cast<const uint32_t*>(ml)[16], ored, ml, ml + 8,
+                        reinterpret_cast<float*>(smem));
 }
 
-// FLAT is a compile-time switch so that the uniform-mode kernel carries no segment-loop state in registers.
-template <int G, bool FLAT>
+// MODE is a compile-time switch: 0 = uniform plan + ticket merge, 1 = flat plan + ticket merge, 2 = uniform plan +
+// flagged merge.  (The uniform kernels carry no segment-loop state in registers; the ticket kernels carry none of
+// the flagged protocol's code: sharing instantiations cost 2-3 % through register pressure.)
+template <int G, int MODE>
 __global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 ? 2 : 1))) sparse_decode_attn_kernel(const __grid_constant__ DecodeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     // 1-D grid, long CTAs first: all compressed splits of all units, then the short window splits.
@@ -887,12 +966,13 @@ __global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 
     const int nblk = a.p.comp_len / kBlockTokens;
     const int id = blockIdx.x;
     const int n_base = a.n_csplit * units;  // uniform mode: CTAs [0, n_base) = split-major, then one extra split for units < n_extra
+    constexpr bool FLAT = MODE == 1, FLAGGED = MODE == 2;
     const int n_comp = FLAT ? a.flat_ctas : n_base + a.n_extra;
     if (id < n_comp) {
         if constexpr (!FLAT) {  // uniform mode: split `id / units` of unit `id % units`
             const int unit = id < n_base ? id % units : id - n_base, split = id < n_base ? id / units : a.n_csplit;
             const int nc = unit_csplits(a, unit);
-            compressed_split<G>(a, smem, unit, split, nc + a.n_wsplit, split * nblk / nc, (split + 1) * nblk / nc, false);
+            compressed_split<G, FLAGGED>(a, smem, unit, split, nc + a.n_wsplit, split * nblk / nc, (split + 1) * nblk / nc, false);
         } else {
             // flat mode: an even cut of all units*nblk blocks, processed as segments cut at unit boundaries (one partial
             // per segment).  The segment arithmetic is redone per segment from opaque copies of (id, j) so that nothing
@@ -906,7 +986,7 @@ __global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 
                 const int b0 = jv == 0 ? cur - u0 : 0;
                 const int b1 = min(static_cast<uint32_t>(nblk), end - u0);
                 const bool more = u0 + nblk < end;
-                compressed_split<G>(a, smem, unit, idv - static_cast<int>(flat_owner(a, u0)), unit_csplits(a, unit) + a.n_wsplit,
+                compressed_split<G, FLAGGED>(a, smem, unit, idv - static_cast<int>(flat_owner(a, u0)), unit_csplits(a, unit) + a.n_wsplit,
                                     b0, b1, j > 0);
                 if (!more) break;
             }
@@ -914,7 +994,7 @@ __global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 
     } else {  // dense-window chunks come after all compressed CTAs
         const int unit = (id - n_comp) % units, wchunk = (id - n_comp) / units;
         const int nc = unit_csplits(a, unit);
-        window_split<G>(a, smem, unit, nc + wchunk, nc + a.n_wsplit, wchunk);
+        window_split<G, FLAGGED>(a, smem, unit, nc + wchunk, nc + a.n_wsplit, wchunk);
     }
     if (threadIdx.x == 0) MFB_TRACE_AT(10);
 }
@@ -930,14 +1010,14 @@ static int pick_slot_nz_bytes(const mfb200_decode_params* p) {
 
 static int pick_depth(int slot_nz_bytes) { return slot_nz_bytes <= 8 * 1024 ? 3 : 2; }
 
-template <int G, bool FLAT>
+template <int G, int MODE>
 static int launch_decode(const DecodeArgs& a, cudaStream_t s) {
     const SmemMap sm = smem_map(G, a.slot_nz_bytes, a.depth);
     size_t smem = (a.n_csplit > 0 || a.n_extra > 0 || a.flat_ctas > 0) ? sm.total : 0;
     if (a.n_wsplit > 0) smem = smem > window_smem_bytes(G) ? smem : window_smem_bytes(G);
     static size_t configured = 0;
     if (smem > configured) {
-        MFB_CUDA(cudaFuncSetAttribute(sparse_decode_attn_kernel<G, FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MFB_CUDA(cudaFuncSetAttribute(sparse_decode_attn_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
         configured = smem;
     }
@@ -952,7 +1032,7 @@ static int launch_decode(const DecodeArgs& a, cudaStream_t s) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (a.p.flags & MFB200_F_PDL) ? 1 : 0;
-    MFB_CUDA(cudaLaunchKernelEx(&cfg, sparse_decode_attn_kernel<G, FLAT>, a));
+    MFB_CUDA(cudaLaunchKernelEx(&cfg, sparse_decode_attn_kernel<G, MODE>, a));
     return launch_status("sparse_decode_attn_kernel");
 }
 
@@ -962,7 +1042,7 @@ using namespace mfb;
 
 namespace mfb {
 struct Plan {
-    int n_csplit, n_extra, n_wsplit, flat_ctas, flat_q, flat_r, max_split;
+    int n_csplit, n_extra, n_wsplit, flat_ctas, flat_q, flat_r, max_split, flagged;
 };
 // Work decomposition of one launch.  Every CTA of a small launch should be resident at once (a second, nearly
 // empty wave doubles the time of a batch-1 launch); window CTAs are short and dispatched last, so only a
@@ -971,7 +1051,7 @@ struct Plan {
 //  * flat mode (24..256 blocks per CTA): the launch's units*nblk blocks are divided evenly over exactly the
 //    resident CTA slots, CTAs may cross unit boundaries -> no wave-quantisation loss for mid-size batches.
 static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count) {
-    Plan pl = {0, 0, (win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit, 0, 0, 0, 0};
+    Plan pl = {0, 0, (win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit, 0, 0, 0, 0, 0};
     const int64_t units = static_cast<int64_t>(batch) * kv_heads;
     const int nblk = comp_len / kBlockTokens;
     if (nblk > 0) {
@@ -1010,6 +1090,8 @@ static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win
         if (per_unit == target / units && per_unit < nblk) pl.n_extra = static_cast<int>(target % units);
     }
     pl.max_split = pl.n_csplit + (pl.n_extra > 0 ? 1 : 0) + pl.n_wsplit;
+    // short launches (every compressed CTA resident from the start, <= 16 blocks each): the merge tail matters
+    pl.flagged = (nblk == 0 || (nblk + pl.n_csplit - 1) / pl.n_csplit <= 16) ? 1 : 0;
     return pl;
 }
 static int device_sm_count(int* out) {
@@ -1041,9 +1123,9 @@ extern "C" int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_
     const int64_t units = static_cast<int64_t>(batch) * kv_heads;
     MFB_REQUIRE(units <= (1 << 20), "decode_plan: batch*kv_heads=%lld exceeds 2^20", static_cast<long long>(units));
     const Plan pl = make_plan(batch, kv_heads, groups, comp_len, win_len, sm_count);
-    const size_t cbytes = (static_cast<size_t>(units) * 4 + 255) & ~static_cast<size_t>(255);
+    const size_t cbytes = 2 * ws_counter_bytes(static_cast<size_t>(units));
     if (counter_bytes) *counter_bytes = cbytes;
-    if (workspace_bytes) *workspace_bytes = cbytes + static_cast<size_t>(units) * pl.max_split * groups * kPartStride * 4;
+    if (workspace_bytes) *workspace_bytes = cbytes + static_cast<size_t>(units) * pl.max_split * groups * kPartStride * 8;
     return pl.max_split;  // partial slots per unit (informational; the launch re-derives the plan itself)
 }
 
@@ -1091,14 +1173,15 @@ extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb
     a.flat_q = pl.flat_q;
     a.flat_r = pl.flat_r;
     a.max_split = pl.max_split;
+    a.flagged = pl.flagged;
     a.slot_nz_bytes = pick_slot_nz_bytes(p);
     a.depth = pick_depth(a.slot_nz_bytes);
     auto s = static_cast<cudaStream_t>(stream);
     switch (p->groups) {
-        case 1: return a.flat_ctas > 0 ? launch_decode<1, true>(a, s) : launch_decode<1, false>(a, s);
-        case 2: return a.flat_ctas > 0 ? launch_decode<2, true>(a, s) : launch_decode<2, false>(a, s);
-        case 4: return a.flat_ctas > 0 ? launch_decode<4, true>(a, s) : launch_decode<4, false>(a, s);
-        default: return a.flat_ctas > 0 ? launch_decode<8, true>(a, s) : launch_decode<8, false>(a, s);
+        case 1: return a.flat_ctas > 0 ? launch_decode<1, 1>(a, s) : (a.flagged ? launch_decode<1, 2>(a, s) : launch_decode<1, 0>(a, s));
+        case 2: return a.flat_ctas > 0 ? launch_decode<2, 1>(a, s) : (a.flagged ? launch_decode<2, 2>(a, s) : launch_decode<2, 0>(a, s));
+        case 4: return a.flat_ctas > 0 ? launch_decode<4, 1>(a, s) : (a.flagged ? launch_decode<4, 2>(a, s) : launch_decode<4, 0>(a, s));
+        default: return a.flat_ctas > 0 ? launch_decode<8, 1>(a, s) : (a.flagged ? launch_decode<8, 2>(a, s) : launch_decode<8, 0>(a, s));
     }
 }
 
@@ -1118,7 +1201,7 @@ extern "C" size_t mfb200_decode_workspace_max(int batch, int kv_heads, int group
         if (sm_count <= 0 && device_sm_count(&sm_count) != MFB200_OK) sm_count = 148;
         const size_t units = static_cast<size_t>(batch) * kv_heads;
         const size_t per_unit = static_cast<size_t>(sm_count) * 3 / units + 4 + (max_win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit;
-        const size_t bound = ((units * 4 + 255) & ~static_cast<size_t>(255)) + units * per_unit * groups * kPartStride * 4;
+        const size_t bound = 2 * ws_counter_bytes(units) + units * per_unit * groups * kPartStride * 8;
         if (bound > best) best = bound;
     }
     return best + 4096;
