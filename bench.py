@@ -45,14 +45,37 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed regions (B200_PROFILING.md).  NVML in a thread (a few
+    ms period: the timed regions are only tens of ms long); `nvidia-smi -lms` as a fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml = index, [], None, None
+        self.sm, self.mask, self.max_mhz, self._stop = [], 0, None, False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            pr = torch.cuda.get_device_properties(self.index)
+            bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.max_mhz = self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -61,11 +84,29 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                self.sm.append(int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.mask |= int(get_reasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.003)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop = True
+            self.t.join(timeout=1.0)
+            sm = sorted(self.sm)
+            reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml, 3 ms period, all timed regions"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -74,7 +115,8 @@ class ClockSampler:
         mx = max([int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()] or [0])
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm),
+                "source": "nvidia-smi -lms 100"}
 
 
 def build_pruned_dense(seed, heads, ctx, L, sparsity):
@@ -238,7 +280,6 @@ def run_ours(args):
     bytes_before = caches[0].compressed_bytes()
     ms_dev = timed(lambda i: step_device(dev_views[nxt() % NSETS]), K)
     gpu_launches = launches[0]
-    clocks = sampler.stop()
 
     # ---- (2) dominant kernel alone: 32 attends per step at the current state, CUDA events on the launch stream
     algo_bytes = caches[0].compressed_bytes()
@@ -271,6 +312,7 @@ def run_ours(args):
     for _ in range(W):
         step_e2e(0)
     ms_e2e = timed(step_e2e, K)
+    clocks = sampler.stop()  # sampled across all three timed regions
 
     peaks = {}
     try:

@@ -5,12 +5,13 @@
 // cat -> /sqrt(d) -> +mask -> fp32 softmax -> F.pad(P) -> torch.cat(NZ) -> Value_Kernel -> window matmul ->
 // add, and the (never launched) SplitK_Reduction (kernel/csrc/Reduction_Kernel.cuh:26-48).
 //
-// Work decomposition: unit = (sequence, KV head); the compressed length is cut into `n_csplit`
-// contiguous ranges of 64-token blocks, the dense window into ranges of <= 64 tokens; grid =
-// n_split * units CTAs (compressed splits first).  Each CTA keeps flash-decoding state (m, l, o), writes one fp32 partial and the
-// last CTA of a unit (atomic ticket) merges the partials -> single launch, no second kernel,
-// graph-capturable.  All G query heads of a KV head are served by the same CTA, so the compressed
-// bytes of a KV head cross HBM once (the reference re-reads them G times, SpMM_Kernel.cuh:175).
+// Work decomposition: unit = (sequence, KV head).  The compressed length is cut into contiguous ranges of 64-token
+// blocks - per unit (uniform plan) or across all units (flat plan, large MHA launches) -, the dense window into
+// ranges of <= 64 tokens; 1-D grid, compressed CTAs first.  Each CTA keeps flash-decoding state (m, l, o) and
+// contributes one fp32 partial per unit it touches; the partials of a unit are merged inside the same launch
+// (ticket or flagged protocol, see publish_or_merge) -> single launch, no second kernel, graph-capturable.
+// All G query heads of a KV head are served by the same CTA, so the compressed bytes of a KV head cross HBM once
+// (the reference re-reads them G times, SpMM_Kernel.cuh:175).
 //
 // A compressed-split CTA is warp-specialised and has NO CTA-wide barrier in its steady state:
 //   warp 9      producer : one lane issues cp.async.bulk (TMA engine) copies of each block's K item and
@@ -20,9 +21,10 @@
 //   warp 8      softmax  : sums the 4 partials, online-softmax update, publishes p[64] and the
 //                          rescale factor.
 //   warps 4-7   V role   : 32 tiles each (one channel half x 32 tokens) -> o accumulators.
-// Every hand-off (slot full/empty, scores full/empty, probabilities full/empty) is an mbarrier, so
-// the K warps run ahead of the V warps by up to two blocks and nobody waits for the slowest warp.
-// Nothing dense is ever rebuilt in shared memory (sparse_tile.cuh).
+// Hand-offs are mbarriers (TMA completion, one -> many signals) or hardware named barriers (many -> one signals,
+// see struct Bars), so the K warps run ahead of the V warps by up to two blocks and nobody waits for the slowest
+// warp.  Nothing dense is ever rebuilt in shared memory for G <= 2 (sparse_tile.cuh); G >= 4 contracts a per-warp
+// dense buffer on the tensor cores (gqa_mma.cuh).
 #include <stdlib.h>
 
 #include "gqa_mma.cuh"
