@@ -229,6 +229,52 @@ def test_fused_attention_vs_oracle(b, hkv, groups, T, sparsity):
     assert torch.equal(got, got2)
 
 
+def _random_geometries(n, seed):
+    """Seeded sweep over the planner's regimes: more units than CTA slots, ragged per-unit splits, the boundary
+    between the flagged and the ticket merge (16 blocks per compressed CTA), tiny and full windows, every G."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        g = int(rng.choice([1, 1, 2, 4, 8]))
+        hkv = int(rng.choice([1, 2, 3, 8, 32]))
+        b = int(rng.choice([1, 1, 2, 5, 16]))
+        while b * hkv * g > 512:
+            b = max(1, b // 2)
+        blocks = int(rng.choice([1, 2, 4, 17, 33, 70]))
+        while b * hkv * blocks * 64 > 160000:  # keep the numpy oracle fast
+            blocks = max(1, blocks // 2)
+        T = 32 + blocks * 64 + int(rng.integers(0, 256))  # L = 256 * floor(...) <= blocks * 64, window 32..287+
+        out.append((b, hkv, g, T, float(rng.choice([0.5, 0.7, 0.9]))))
+    return out
+
+
+@pytest.mark.parametrize("b,hkv,groups,T,sparsity", _random_geometries(14, seed=2024) + [
+    (16, 32, 1, 352, 0.5),    # 512 units: more units than resident CTA slots, one compressed CTA per unit
+    (1, 1, 1, 2600, 0.7),     # a single unit cut into one-block splits (flagged merge, 40+ partials)
+    (2, 32, 1, 8736, 0.7),    # uniform plan with 23 blocks per CTA: ticket merge (just below the flat threshold)
+])
+def test_fused_attention_random_geometries(b, hkv, groups, T, sparsity):
+    cache, q, kp, vp, L = _attention_case(b, hkv, groups, T, sparsity, seed=7 * T + b)
+    _check_attention(cache.attend(q.cuda()), q, kp, vp, L)
+    # three fused decode steps (append + attention) on top, checked against the grown dense cache
+    g = torch.Generator().manual_seed(T)
+    for _ in range(3):
+        kn = torch.randn(b, hkv, 1, 128, generator=g).to(torch.float16)
+        vn = torch.randn(b, hkv, 1, 128, generator=g).to(torch.float16)
+        qn = torch.randn(b, hkv * groups, 1, 128, generator=g).to(torch.float16)
+        out = cache.decode_step(qn.cuda(), kn.cuda(), vn.cuda())
+        kp, vp = np.concatenate([kp, kn.numpy()], axis=2), np.concatenate([vp, vn.numpy()], axis=2)
+        if cache.comp_len != L:  # the step crossed the compression schedule: those 256 rows are pruned from now on
+            kp[:, :, L:cache.comp_len] = O.prune_rows(kp[:, :, L:cache.comp_len], sparsity)
+            vp[:, :, L:cache.comp_len] = O.prune_rows(vp[:, :, L:cache.comp_len], sparsity)
+            L = cache.comp_len
+    # the last output was computed before that step's (possible) compression
+    dense = O.masked_dense_attention(qn.numpy(), kp, vp).astype(np.float32)
+    d = np.abs(out.float().cpu().numpy() - dense)
+    assert d.max() <= MAX_ABS and d.mean() <= MEAN_ABS, (d.max(), d.mean())
+    cache.check_overflow()
+
+
 def test_fused_attention_mask():
     b, hkv, groups, T = 2, 2, 2, 700
     cache, q, kp, vp, L = _attention_case(b, hkv, groups, T, 0.5, seed=77)
