@@ -178,7 +178,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "tok/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": max(1, min(args.warmup, 3)), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "inputs larger than L2/L3"},
+            "config": {"workload": WORKLOAD, "global_batch": 1, "layers": args.layers, "context": CTX,
+                       "l2": "inputs larger than the host L2/L3 (4 distinct 268 MB layer caches cycled)",
+                       "partition": "rank 0 only (CPU arm)"},
             "cpu_baseline": {"value": val, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

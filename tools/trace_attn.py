@@ -5,7 +5,7 @@
 Launches the 32-layer back-to-back sequence the bench times (PDL + early KV prefetch), then prints, for the
 last two launches, when each phase of the compressed CTAs happened relative to the first CTA's start.
 Slots: 0 entry, 1 idx+barriers ready, 2 PDL wait passed, 3 q staged, 4/5 K warp first/last block done,
-6/7 V warp first/last block done, 8 roles joined, 9 ticket taken, 10 exit, 11 smid, 12 blocks, 13 merged.
+6/7 V warp first/last block done, 8 roles joined, 9 partial published / ticket taken, 10 exit, 11 smid, 12 blocks, 13 merged.
 """
 import ctypes as C
 import sys
@@ -53,7 +53,7 @@ def main():
     buf = np.zeros((2, n, 16), dtype=np.uint64)
     slots = raw.mfb200_debug_trace(buf.ctypes.data, n)
     assert slots == 16
-    names = ["entry", "idx+bars", "pdl wait", "q staged", "K first", "K last", "V first", "V last", "joined", "ticket", "exit"]
+    names = ["entry", "idx+bars", "pdl wait", "q staged", "K first", "K last", "V first", "V last", "joined", "published", "exit"]
     t_first = None
     for half in range(2):
         t = buf[half].astype(np.int64)
@@ -76,7 +76,7 @@ def main():
         merged = tc[tc[:, 13] == 1]
         if len(merged):
             d = (merged[:, 10] - merged[:, 9]) / 1e3
-            print(f"  merge (ticket -> exit) of the {len(merged)} merging compressed CTAs: p50 {np.median(d):.2f} max {d.max():.2f} us")
+            print(f"  merge (published -> exit) of the {len(merged)} merging compressed CTAs: p50 {np.median(d):.2f} max {d.max():.2f} us")
         per_blk = (tc[:, 7] - tc[:, 3]) / 1e3 / np.maximum(tc[:, 12], 1)
         print(f"  (V last - q staged) / blocks: p50 {np.median(per_blk):.2f} us/block")
         sm = np.bincount(t[:, 11].astype(int), minlength=148)
