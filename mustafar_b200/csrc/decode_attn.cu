@@ -1046,9 +1046,8 @@ namespace mfb {
 struct Plan {
     int n_csplit, n_extra, n_wsplit, flat_ctas, flat_q, flat_r, max_split, flagged;
 };
-// Work decomposition of one launch.  Every CTA of a small launch should be resident at once (a second, nearly
-// empty wave doubles the time of a batch-1 launch); window CTAs are short and dispatched last, so only a
-// fraction of a slot is reserved for each.
+// Work decomposition of one launch.  The compressed CTAs of a small launch should all be resident at once (a second,
+// nearly empty wave doubles the time of a batch-1 launch); the short window CTAs are dispatched last.
 //  * uniform mode: every unit is cut into the same number of compressed splits;
 //  * flat mode (24..256 blocks per CTA): the launch's units*nblk blocks are divided evenly over exactly the
 //    resident CTA slots, CTAs may cross unit boundaries -> no wave-quantisation loss for mid-size batches.
@@ -1058,9 +1057,9 @@ static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win
     const int nblk = comp_len / kBlockTokens;
     if (nblk > 0) {
         const int64_t slots = static_cast<int64_t>(sm_count) * (groups <= 1 ? MFB_G1_CTAS : (groups <= 4 ? 2 : 1));
-        int64_t reserve = (units * pl.n_wsplit + 3) / 4;
-        if (reserve > slots / 8) reserve = slots / 8;
-        const int64_t avail = slots - reserve;
+        // No slots are held back for the window CTAs: they are short, trail the compressed CTAs in the grid and take
+        // the slots of the first compressed CTAs that finish (a reserve of up to slots/8 measured 2 % slower at batch 1).
+        const int64_t avail = slots;
         const int64_t B = units * nblk;
         // testing / tuning override (not API): MFB200_FLAT=0 never uses the flat mode, MFB200_FLAT=n forces n CTAs
         static const int forced_flat = [] { const char* e = getenv("MFB200_FLAT"); return e ? atoi(e) : -1; }();
