@@ -1068,8 +1068,22 @@ static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win
         int64_t n_flat = 0;
         if (forced_flat > 0) n_flat = forced_flat;
         else if (forced_flat < 0) {
-            // (G >= 4 launches measured no gain from the flat cut: they are not limited by the tail)
-            if (groups <= 2) n_flat = B / (2 * slots) >= 48 ? 2 * slots : (B / slots >= 24 ? slots : 0);
+            if (groups <= 2) {
+                n_flat = B / (2 * slots) >= 48 ? 2 * slots : (B / slots >= 24 ? slots : 0);
+            } else {
+                // G >= 4 (2 or 1 CTAs per SM): the flat cut pays when the uniform plan's busiest slot carries > 5 % more
+                // blocks than an even cut would (config 3: 2 splits of 62 blocks per unit on 296 slots vs 54 blocks
+                // per CTA: 168 -> 156 us); k full waves when one wave would exceed the per-CTA block limit.
+                const int64_t k = ((B + slots - 1) / slots + kMaxBlocksPerSplit - 1) / kMaxBlocksPerSplit;
+                const int64_t n = k * slots;
+                const int64_t min_c = (nblk + kMaxBlocksPerSplit - 1) / kMaxBlocksPerSplit;
+                int64_t per_unit = slots / units;
+                if (per_unit < min_c) per_unit = min_c;
+                if (per_unit > nblk) per_unit = nblk;
+                const int64_t waves_u = (units * per_unit + slots - 1) / slots;
+                const int64_t busiest_u = waves_u * ((nblk + per_unit - 1) / per_unit), busiest_f = k * ((B + n - 1) / n);
+                if (B / n >= 24 && busiest_u * 20 > busiest_f * 21) n_flat = n;
+            }
         }
         if (n_flat > B) n_flat = B;
         if (n_flat > 0 && B < (int64_t{1} << 31) && (B + n_flat - 1) / n_flat <= kMaxBlocksPerSplit) {
