@@ -424,8 +424,8 @@ __device__ __forceinline__ int32_t lookback_exclusive(unsigned long long* st, in
 }
 
 template <int LAYOUT>
-__device__ __forceinline__ void prefill_block_body(const PrefillArgs& a, int which, uint16_t* tile, uint32_t* bm_hi,
-                                                   uint32_t* bm_lo, uint16_t (*stage)[64]) {
+__device__ __forceinline__ void prefill_block_body(const PrefillArgs& a, int which, uint16_t* tile,
+                                                   uint16_t (*stage)[16][64]) {
     __shared__ int32_t warp_tot[8];
     __shared__ int32_t s_excl;
     const int tb = blockIdx.x;
@@ -447,16 +447,27 @@ __device__ __forceinline__ void prefill_block_body(const PrefillArgs& a, int whi
             dst[1] = v[i].y;
         }
     }
+    // the warp's packing area: 16 tiles x 64 halves, zero = the padding behind each tile's nonzeros
+    {
+        uint32_t* z = reinterpret_cast<uint32_t*>(stage[warp]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i * 32 + lane] = 0;
+    }
     __syncthreads();
-    // 2. bitmaps + padded counts: warp w owns tiles 16w .. 16w+15, lane i < 16 keeps tile 16w+i
+    // 2. bitmaps + padded counts + packing in ONE pass over the tile's elements: warp w owns tiles 16w .. 16w+15,
+    //    lane i < 16 keeps the bitmap of tile 16w+i; every lane drops its two elements at their rank in the packing area
     const int t0 = warp * 16;
+    const uint32_t above = lane == 0 ? 0u : (0xffffffffu << (32 - lane));  // bits of elements before mine
     uint32_t my_hi = 0, my_lo = 0;
 #pragma unroll 4
     for (int i = 0; i < 16; ++i) {
         uint32_t e0, e1;
         tile_elems<LAYOUT>(tile, t0 + i, lane, e0, e1);
-        const uint32_t hi = __brev(__ballot_sync(0xffffffffu, (e0 & 0x7fffu) != 0));
-        const uint32_t lo = __brev(__ballot_sync(0xffffffffu, (e1 & 0x7fffu) != 0));
+        const bool nz0 = (e0 & 0x7fffu) != 0, nz1 = (e1 & 0x7fffu) != 0;
+        const uint32_t hi = __brev(__ballot_sync(0xffffffffu, nz0));
+        const uint32_t lo = __brev(__ballot_sync(0xffffffffu, nz1));
+        if (nz0) stage[warp][i][__popc(hi & above)] = static_cast<uint16_t>(e0);
+        if (nz1) stage[warp][i][__popc(hi) + __popc(lo & above)] = static_cast<uint16_t>(e1);
         if (lane == static_cast<uint32_t>(i)) {
             my_hi = hi;
             my_lo = lo;
@@ -465,8 +476,6 @@ __device__ __forceinline__ void prefill_block_body(const PrefillArgs& a, int whi
     const int64_t tile_g = a.tile_offset + static_cast<int64_t>(tb) * 128 + t0 + lane;  // lanes < 16
     int32_t cnt = 0;
     if (lane < 16) {
-        bm_hi[t0 + lane] = my_hi;
-        bm_lo[t0 + lane] = my_lo;
         a.bmp[which][u * a.bmp_stride + tile_g] = static_cast<int64_t>((static_cast<uint64_t>(my_hi) << 32) | my_lo);
         cnt = ((__popc(my_hi) + __popc(my_lo) + 7) & ~7) >> 1;
     }
@@ -497,39 +506,25 @@ __device__ __forceinline__ void prefill_block_body(const PrefillArgs& a, int whi
     for (int w = 0; w < warp; ++w) base += warp_tot[w];
     if (lane < 16) idx[tile_g + 1] = base + incl;
     const int32_t my_off = base + incl - cnt;  // lanes < 16: offset of tile t0 + lane (2-half units)
-    // 4. pack: one contiguous (<= 128 B) store per tile
-    const uint32_t above = lane == 0 ? 0u : (0xffffffffu << (32 - lane));
-    const uint32_t mybit = 0x80000000u >> lane;
+    // 4. copy out: one contiguous (<= 128 B) store per tile
     uint16_t* out = reinterpret_cast<uint16_t*>(a.nz[which]) + a.head_base[which][u];
-    uint32_t* st32 = reinterpret_cast<uint32_t*>(stage[warp]);
-#pragma unroll 2
+#pragma unroll 4
     for (int i = 0; i < 16; ++i) {
-        const uint32_t hi = __shfl_sync(0xffffffffu, my_hi, i), lo = __shfl_sync(0xffffffffu, my_lo, i);
         const int32_t o2 = __shfl_sync(0xffffffffu, my_off, i);
-        uint32_t e0, e1;
-        tile_elems<LAYOUT>(tile, t0 + i, lane, e0, e1);
-        st32[lane] = 0;
-        __syncwarp();
-        const uint32_t pc_hi = __popc(hi);
-        if (hi & mybit) stage[warp][__popc(hi & above)] = static_cast<uint16_t>(e0);
-        if (lo & mybit) stage[warp][pc_hi + __popc(lo & above)] = static_cast<uint16_t>(e1);
-        __syncwarp();
-        const uint32_t n_pad = (pc_hi + __popc(lo) + 7u) & ~7u;
+        const uint32_t n_pad = 2u * static_cast<uint32_t>(__shfl_sync(0xffffffffu, cnt, i));  // halves
         if (a.head_capacity > 0 && 2 * static_cast<int64_t>(o2) + n_pad > a.head_capacity) {
             if (lane == 0 && a.overflow != nullptr) atomicExch(a.overflow, 1);
         } else if (2 * lane < n_pad) {
-            reinterpret_cast<uint32_t*>(out + 2 * static_cast<int64_t>(o2))[lane] = st32[lane];
+            reinterpret_cast<uint32_t*>(out + 2 * static_cast<int64_t>(o2))[lane] = reinterpret_cast<const uint32_t*>(stage[warp][i])[lane];
         }
-        __syncwarp();
     }
 }
 
 __global__ void __launch_bounds__(kCompressThreads) compress_prefill_kernel(const PrefillArgs a) {
     __shared__ __align__(16) uint16_t tile[64 * kPitch];
-    __shared__ __align__(16) uint16_t stage[8][64];
-    __shared__ uint32_t bm_hi[128], bm_lo[128];
-    if (blockIdx.z == 0) prefill_block_body<MFB200_LAYOUT_KEY>(a, 0, tile, bm_hi, bm_lo, stage);
-    else prefill_block_body<MFB200_LAYOUT_VALUE>(a, 1, tile, bm_hi, bm_lo, stage);
+    __shared__ __align__(16) uint16_t stage[8][16][64];  // per warp: its 16 tiles, packed and zero-padded
+    if (blockIdx.z == 0) prefill_block_body<MFB200_LAYOUT_KEY>(a, 0, tile, stage);
+    else prefill_block_body<MFB200_LAYOUT_VALUE>(a, 1, tile, stage);
 }
 
 // ---- window append: win[u, pos, :] = row[u, :] (K and V in one launch) -------------------------

@@ -18,6 +18,8 @@ CFG = {
     "cfg5s": dict(b=4, hkv=8, g=4, t=32768, s=0.5),    # config 5 at 1/8 of the batch
     "mid1": dict(b=8, hkv=32, g=1, t=4096, s=0.5),     # mid-size MHA launches: 256 units
     "mid2": dict(b=32, hkv=8, g=1, t=8192, s=0.7),
+    "mid3": dict(b=2, hkv=32, g=1, t=4096, s=0.5),     # 64 units x 60 blocks: 8.6 blocks per CTA slot
+    "mid4": dict(b=4, hkv=32, g=1, t=4096, s=0.5),     # 128 units x 60 blocks: 17.3 blocks per CTA slot
 }
 
 
