@@ -1202,22 +1202,19 @@ extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb
 
 extern "C" size_t mfb200_decode_workspace_max(int batch, int kv_heads, int groups, int max_comp_len, int max_win_len,
                                               int sm_count) {
+    // The number of partial slots per unit is not monotone in the lengths (ragged splits, the switch between the
+    // uniform and the flat plan, k-wave flat plans): take the maximum over EVERY (compressed length, window chunk
+    // count) the cache can pass through.  Pure host arithmetic, a few microseconds per thousand tokens of capacity.
+    if (sm_count <= 0 && device_sm_count(&sm_count) != MFB200_OK) sm_count = 148;
     size_t best = 0;
-    // n_split is not monotone in the lengths (the window reserve eats into the compressed splits): scan the few
-    // window-chunk counts at the largest compressed length, and the largest window at every chunk boundary.
-    for (int lw = 0; lw <= max_win_len; lw += kWinTokensPerSplit) {
-        size_t ws = 0;
-        const int w = lw == 0 ? (max_comp_len > 0 ? 0 : 1) : lw;
-        if (mfb200_decode_plan(batch, kv_heads, groups, max_comp_len - max_comp_len % 64, w, sm_count, &ws, nullptr) > 0 && ws > best) best = ws;
-    }
-    size_t ws = 0;
-    if (mfb200_decode_plan(batch, kv_heads, groups, max_comp_len - max_comp_len % 64, max_win_len > 0 ? max_win_len : 1, sm_count, &ws, nullptr) > 0 && ws > best) best = ws;
-    {   // closed-form bound on the partial slots per unit over all shorter contexts (splits never exceed slots/units + 2)
-        if (sm_count <= 0 && device_sm_count(&sm_count) != MFB200_OK) sm_count = 148;
-        const size_t units = static_cast<size_t>(batch) * kv_heads;
-        const size_t per_unit = static_cast<size_t>(sm_count) * 3 / units + 4 + (max_win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit;
-        const size_t bound = 2 * ws_counter_bytes(units) + units * per_unit * groups * kPartStride * 8;
-        if (bound > best) best = bound;
+    const int max_nw = (max_win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit;
+    for (int comp = 0; comp <= max_comp_len - max_comp_len % kBlockTokens; comp += kBlockTokens) {
+        for (int nw = (comp > 0 ? 0 : 1); nw <= (max_nw > 0 ? max_nw : 1); ++nw) {
+            int win = nw * kWinTokensPerSplit;
+            if (win > max_win_len) win = max_win_len > 0 ? max_win_len : 1;
+            size_t ws = 0;
+            if (mfb200_decode_plan(batch, kv_heads, groups, comp, win, sm_count, &ws, nullptr) > 0 && ws > best) best = ws;
+        }
     }
     return best + 4096;
 }
