@@ -146,7 +146,8 @@ typedef struct mfb200_decode_params {
     int32_t slot_kb;      /* staging capacity for one 64-token block's nonzeros, KB (1..16); 0 = 16
                              (worst case, every element kept).  Larger blocks still work: they take a
                              slower path that reads their nonzeros straight from global memory. */
-    int32_t reserved;
+    int32_t workspace_kb; /* size of `workspace` in KB (rounded down); 0 = not checked.  When set, a launch whose plan needs
+                             more is refused with MFB200_EINVAL instead of writing past the buffer. */
     /* query / output: fp16 [B, Hq, 128] contiguous */
     const void* q;
     void* out;

@@ -29,7 +29,7 @@ class DecodeParams(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("kv_heads", C.c_int32), ("groups", C.c_int32), ("comp_len", C.c_int32),
         ("win_len", C.c_int32), ("flags", C.c_int32), ("score_div", C.c_float), ("n_split", C.c_int32),
-        ("slot_kb", C.c_int32), ("reserved", C.c_int32),
+        ("slot_kb", C.c_int32), ("workspace_kb", C.c_int32),
         ("q", _vp), ("out", _vp),
         ("k_bmp", _vp), ("k_idx", _vp), ("k_nz", _vp), ("k_nz_off", _vp),
         ("v_bmp", _vp), ("v_idx", _vp), ("v_nz", _vp), ("v_nz_off", _vp),

@@ -214,6 +214,7 @@ class MustafarKVCache:
                 self._ws = torch.zeros((nbytes,), dtype=torch.uint8, device=self.device)
             self._ws_bytes = nbytes
             self._p.workspace = self._ws.data_ptr()
+            self._p.workspace_kb = nbytes // 1024  # the library refuses launches that would need more
             self._p_ref = C.byref(self._p)
             self._step = lib.mfb200_decode_step
         return self._p

@@ -131,7 +131,7 @@ __device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepco
 // Timeline instrumentation (`make trace`, tools/trace_attn.py): per-CTA phase timestamps from %globaltimer.
 #ifdef MFB_TRACE
 constexpr int kTraceSlots = 16, kTraceMaxCtas = 8192;
-__device__ unsigned long long g_trace[2 * kTraceMaxCtas * kTraceSlots];  // two launches: params.reserved & 1 picks the half
+__device__ unsigned long long g_trace[2 * kTraceMaxCtas * kTraceSlots];  // two launches: flag bit 0x100 picks the half
 __shared__ int s_trace_half;  // set by thread 0 at kernel entry (barriers follow before any other thread traces)
 __device__ __forceinline__ void trace_val(int k, unsigned long long v) {
     const int s_half = s_trace_half;
@@ -956,7 +956,7 @@ __global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 
 #endif
     if (threadIdx.x == 0) {
 #ifdef MFB_TRACE
-        s_trace_half = a.p.reserved & 1;
+        s_trace_half = (a.p.flags >> 8) & 1;
 #endif
         MFB_TRACE_AT(0);
         unsigned smid;
@@ -1189,6 +1189,12 @@ extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb
     a.flat_r = pl.flat_r;
     a.max_split = pl.max_split;
     a.flagged = pl.flagged;
+    if (p->workspace_kb > 0) {
+        const size_t need = 2 * ws_counter_bytes(static_cast<size_t>(p->batch) * p->kv_heads) +
+                            static_cast<size_t>(p->batch) * p->kv_heads * pl.max_split * p->groups * kPartStride * 8;
+        MFB_REQUIRE(need <= static_cast<size_t>(p->workspace_kb) * 1024, "decode: workspace of %d KB is too small for this launch (%zu bytes needed; size it with mfb200_decode_workspace_max)",
+                    p->workspace_kb, need);
+    }
     a.slot_nz_bytes = pick_slot_nz_bytes(p);
     a.depth = pick_depth(a.slot_nz_bytes);
     auto s = static_cast<cudaStream_t>(stream);

@@ -411,6 +411,22 @@ def test_prefill_long_chain_and_append_offset():
         assert torch.equal(a.nz[:n].view(torch.int16), r.nz[:n].view(torch.int16))
 
 
+def test_launch_refuses_a_workspace_that_is_too_small():
+    import ctypes as C
+    from mustafar_b200 import _lib
+    cache, q, kp, vp, L = _attention_case(1, 4, 1, 1500, 0.5, seed=90)
+    qd = q.cuda()
+    ref = cache.attend(qd).clone()
+    p = cache.make_params(qd.view(1, -1, 128), torch.empty_like(qd))
+    assert p.workspace_kb > 0
+    small = _lib.DecodeParams()
+    C.memmove(C.byref(small), C.byref(p), C.sizeof(p))
+    small.workspace_kb = 1
+    rc = _lib.load().mfb200_sparse_decode_attention(C.byref(small), _lib.stream_ptr())
+    assert rc < 0 and b"workspace" in _lib.load().mfb200_last_error()
+    assert torch.equal(cache.attend(qd), ref)  # the refused launch touched nothing
+
+
 def test_slab_overflow_is_detected_not_corrupting():
     from mustafar_b200.attention import MustafarKVCache
     b, hkv = 1, 2

@@ -44,8 +44,8 @@ def main():
         for p in params:
             lib.mfb200_sparse_decode_attention(C.byref(p), sp)
     torch.cuda.synchronize()
-    # params.reserved & 1 picks the half of the trace buffer: the last launch writes half 1, all others half 0
-    params[-1].reserved = 1
+    # flag bit 0x100 picks the half of the trace buffer: the last launch writes half 1, all others half 0
+    params[-1].flags |= 0x100
     for p in params:
         lib.mfb200_sparse_decode_attention(C.byref(p), sp)
     torch.cuda.synchronize()
