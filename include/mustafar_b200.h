@@ -206,6 +206,10 @@ typedef struct mfb200_decode_params {
  * launches keep it consistent afterwards (tags only grow), so it is graph-replayable. */
 int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count,
                        size_t* workspace_bytes, size_t* counter_bytes);
+/* Host-only self-check of the work decomposition the launch would use for this geometry: every unit's blocks covered
+ * exactly once, per-CTA block limit, unique partial slots inside the workspace stride, merge ownership.  Returns
+ * MFB200_OK or MFB200_EINVAL (mfb200_last_error() names the first inconsistency).  Needs no GPU when sm_count > 0. */
+int mfb200_decode_plan_check(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count);
 int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb200_stream_t stream);
 
 /* One decode step on a long-lived parameter block (the host keeps one per layer cache): sets q / out /

@@ -57,6 +57,7 @@ SIGNATURES = {
     "mfb200_value_formulation": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32]),
     "mfb200_value_workspace_bytes": (C.c_size_t, [_i32, _i32]),
     "mfb200_decode_plan": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "mfb200_decode_plan_check": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "mfb200_sparse_decode_attention": (_i32, [C.POINTER(DecodeParams), _vp]),
     "mfb200_decode_step": (_i32, [C.POINTER(DecodeParams), _vp, _vp, _vp, _vp, _i32, _vp]),
     "mfb200_decode_workspace_max": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32, _i32]),

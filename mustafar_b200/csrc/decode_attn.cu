@@ -1144,6 +1144,112 @@ extern "C" int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_
     return pl.max_split;  // partial slots per unit (informational; the launch re-derives the plan itself)
 }
 
+// Host-side self-check of the work decomposition: walks every CTA of the launch exactly like the kernel entry does
+// (same helpers: flat_start / flat_owner / unit_csplits) and verifies that every unit's blocks are covered exactly
+// once, that no CTA exceeds the per-CTA block limit, that partial slots are unique and inside the workspace stride,
+// and that the flagged merge's owner of the last slot is the unit's highest CTA index.  No GPU involved.
+extern "C" int mfb200_decode_plan_check(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count) {
+    size_t ws = 0;
+    const int rc = mfb200_decode_plan(batch, kv_heads, groups, comp_len, win_len, sm_count > 0 ? sm_count : 148, &ws, nullptr);
+    if (rc < 0) return rc;
+    if (sm_count <= 0) sm_count = 148;
+    const Plan pl = make_plan(batch, kv_heads, groups, comp_len, win_len, sm_count);
+    DecodeArgs a = {};
+    a.p.batch = batch;
+    a.p.kv_heads = kv_heads;
+    a.p.groups = groups;
+    a.p.comp_len = comp_len;
+    a.p.win_len = win_len;
+    a.n_csplit = pl.n_csplit;
+    a.n_extra = pl.n_extra;
+    a.n_wsplit = pl.n_wsplit;
+    a.flat_ctas = pl.flat_ctas;
+    a.flat_q = pl.flat_q;
+    a.flat_r = pl.flat_r;
+    a.max_split = pl.max_split;
+    a.flagged = pl.flagged;
+    const int units = batch * kv_heads, nblk = comp_len / kBlockTokens;
+    MFB_REQUIRE(pl.n_wsplit * kWinTokensPerSplit >= win_len && (pl.n_wsplit - 1) * kWinTokensPerSplit < win_len || win_len == 0,
+                "plan_check: %d window chunks for %d window tokens", pl.n_wsplit, win_len);
+    MFB_REQUIRE(!(pl.flat_ctas > 0 && pl.flagged), "plan_check: flat plan with flagged merge");
+    // per unit: next expected block, bitmap of used slots (max_split <= a few hundred), highest CTA index seen
+    const int n_comp = pl.flat_ctas > 0 ? pl.flat_ctas : pl.n_csplit * units + pl.n_extra;
+    int* next_blk = static_cast<int*>(calloc(units, sizeof(int)));
+    int* n_seg = static_cast<int*>(calloc(units, sizeof(int)));
+    int* last_id = static_cast<int*>(calloc(units, sizeof(int)));
+    int* last_slot_owner = static_cast<int*>(calloc(units, sizeof(int)));
+    unsigned char* used = static_cast<unsigned char*>(calloc(static_cast<size_t>(units) * pl.max_split, 1));
+    int err = 0;
+    auto segment = [&](int id, int unit, int split, int b0, int b1) {
+        const int nc = unit_csplits(a, unit);
+        if (unit < 0 || unit >= units || split < 0 || split >= nc || nc + pl.n_wsplit > pl.max_split || b0 != next_blk[unit] || b1 <= b0 ||
+            b1 > nblk || b1 - b0 > kMaxBlocksPerSplit || used[static_cast<size_t>(unit) * pl.max_split + split]) {
+            if (!err) set_error("plan_check: CTA %d segment (unit %d, slot %d of %d, blocks [%d, %d)) is inconsistent (next block %d, max_split %d)",
+                                id, unit, split, nc, b0, b1, unit >= 0 && unit < units ? next_blk[unit] : -1, pl.max_split);
+            err = 1;
+            return;
+        }
+        used[static_cast<size_t>(unit) * pl.max_split + split] = 1;
+        next_blk[unit] = b1;
+        n_seg[unit] += 1;
+        last_id[unit] = id;
+        if (split == nc + pl.n_wsplit - 1) last_slot_owner[unit] = id;
+    };
+    for (int id = 0; id < n_comp && !err; ++id) {
+        if (pl.flat_ctas == 0) {  // mirrors the uniform branch of the kernel entry
+            const int n_base = pl.n_csplit * units;
+            const int unit = id < n_base ? id % units : id - n_base, split = id < n_base ? id / units : pl.n_csplit;
+            const int nc = unit_csplits(a, unit);
+            // uniform splits of one unit are visited in increasing split order only across ids; order them by block range
+            const int b0 = split * nblk / nc, b1 = (split + 1) * nblk / nc;
+            if (b0 != next_blk[unit]) {  // split-major ids visit split s of every unit before split s+1: always in order
+                if (!err) set_error("plan_check: uniform split %d of unit %d starts at block %d, expected %d", split, unit, b0, next_blk[unit]);
+                err = 1;
+                break;
+            }
+            segment(id, unit, split, b0, b1);
+        } else {  // mirrors the flat branch
+            for (int j = 0;; ++j) {
+                const uint32_t cur = flat_start(a, id), end = cur + a.flat_q + (id < a.flat_r ? 1 : 0);
+                const int unit = cur / static_cast<uint32_t>(nblk) + j;
+                const uint32_t u0 = static_cast<uint32_t>(unit) * nblk;
+                const int b0 = j == 0 ? cur - u0 : 0;
+                const int b1 = static_cast<int>(end - u0 < static_cast<uint32_t>(nblk) ? end - u0 : nblk);
+                segment(id, unit, id - static_cast<int>(flat_owner(a, u0)), b0, b1);
+                if (err || !(u0 + nblk < end)) break;
+            }
+        }
+    }
+    for (int w = 0; w < pl.n_wsplit * units && !err; ++w) {  // window CTAs: chunk-major after all compressed CTAs
+        const int id = n_comp + w, unit = w % units, wchunk = w / units, nc = nblk > 0 ? unit_csplits(a, unit) : 0;
+        const int slot = nc + wchunk;
+        if (slot >= pl.max_split || used[static_cast<size_t>(unit) * pl.max_split + slot]) {
+            set_error("plan_check: window chunk %d of unit %d: slot %d unusable (max_split %d)", wchunk, unit, slot, pl.max_split);
+            err = 1;
+            break;
+        }
+        used[static_cast<size_t>(unit) * pl.max_split + slot] = 1;
+        last_id[unit] = id;
+        if (slot == nc + pl.n_wsplit - 1) last_slot_owner[unit] = id;
+    }
+    for (int u = 0; u < units && !err; ++u) {
+        const int nc = nblk > 0 ? unit_csplits(a, u) : 0;
+        if (next_blk[u] != nblk || n_seg[u] != nc) {
+            set_error("plan_check: unit %d covered up to block %d of %d with %d segments (expected %d)", u, next_blk[u], nblk, n_seg[u], nc);
+            err = 1;
+        } else if (pl.flagged && last_slot_owner[u] != last_id[u]) {
+            set_error("plan_check: unit %d: the owner of the last slot (CTA %d) is not its highest CTA (%d)", u, last_slot_owner[u], last_id[u]);
+            err = 1;
+        }
+    }
+    free(next_blk);
+    free(n_seg);
+    free(last_id);
+    free(last_slot_owner);
+    free(used);
+    return err ? MFB200_EINVAL : MFB200_OK;
+}
+
 extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb200_stream_t stream) {
     MFB_REQUIRE(p != nullptr, "decode: null params");
     MFB_REQUIRE(p->batch > 0 && p->kv_heads > 0, "decode: batch/kv_heads must be positive");

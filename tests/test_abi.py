@@ -93,3 +93,22 @@ def test_workspace_max_covers_every_shorter_context(lib):
                     assert n >= 1, (batch, hkv, g, comp, win)
                     assert ws.value <= ws_max, (batch, hkv, g, comp, win, ws.value, ws_max)
                     assert cb.value >= 2 * 4 * batch * hkv and cb.value % 256 == 0
+
+
+def test_plan_self_check_over_geometries(lib):
+    """mfb200_decode_plan_check walks every CTA of a launch the way the kernel entry does (shared helpers) and verifies
+    coverage, per-CTA block limit, slot uniqueness and merge ownership.  Swept over the planner's regimes on the host."""
+    geoms = [(1, 32, 1), (1, 8, 4), (16, 8, 4), (4, 32, 1), (2, 1, 8), (1, 1, 1), (7, 3, 2), (64, 8, 4), (32, 8, 4), (5, 8, 8),
+             (8, 32, 1), (64, 32, 1), (3, 2, 2)]
+    n = 0
+    for sm in (148, 132, 80):
+        for batch, hkv, g in geoms:
+            for comp in list(range(0, 4097, 64)) + [8192, 16384, 23744, 32512, 65536, 131072]:
+                for win in (0, 1, 64, 65, 288):
+                    if comp == 0 and win == 0:
+                        continue
+                    rc = lib.mfb200_decode_plan_check(batch, hkv, g, comp, win, sm)
+                    assert rc == 0, (sm, batch, hkv, g, comp, win, lib.mfb200_last_error())
+                    n += 1
+    assert n > 10000
+    assert lib.mfb200_decode_plan_check(1, 32, 3, 4096, 64, 148) < 0  # invalid geometry is an error, not a crash
