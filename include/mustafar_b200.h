@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MFB200_ABI_VERSION 1
+#define MFB200_ABI_VERSION 2
 
 #define MFB200_OK 0
 #define MFB200_EINVAL (-1)  /* bad argument (shape, alignment, null pointer) */
@@ -106,8 +106,9 @@ int mfb200_compress_append_chunk(void* k_win, void* v_win, int64_t win_stride, i
  * prunes and compresses tokens [0, tokens) of key_states / value_states (fp16 [batch, kv_heads, >= tokens, 128],
  * arbitrary batch / head / token strides given in halves as {stride_b, stride_h, stride_t}, innermost stride 1)
  * into the cache slabs at tile_offset, K and V in ONE single-pass launch (each input element is read once; block
- * offsets are exchanged between CTAs with a decoupled look-back).  status_ws: 2 * batch * kv_heads * tokens/64 * 8
- * bytes of scratch (zeroed by the call).  Slabs / head_base / head_capacity / overflow as in
+ * offsets are exchanged between CTAs with a decoupled look-back whose block order comes from an atomic ticket, so it does
+ * not depend on the CTA dispatch order).  status_ws: 2 * batch * kv_heads * (tokens/64 + 1) * 8 bytes of scratch (zeroed
+ * by the call).  Slabs / head_base / head_capacity / overflow as in
  * mfb200_compress_append_chunk.  Bit-identical to mfb200_compress_count + _scan + _pack. */
 int mfb200_compress_prefill(const void* k, const void* v, const int64_t* k_strides, const int64_t* v_strides,
                             int batch, int kv_heads, int64_t tokens, int prune_k_key, int prune_k_value,
@@ -148,6 +149,9 @@ typedef struct mfb200_decode_params {
                              slower path that reads their nonzeros straight from global memory. */
     int32_t workspace_kb; /* size of `workspace` in KB (rounded down); 0 = not checked.  When set, a launch whose plan needs
                              more is refused with MFB200_EINVAL instead of writing past the buffer. */
+    int32_t plan_hint;    /* work decomposition: 0 = chosen from the geometry (production), n > 0 = flat plan with n compressed
+                             CTAs, < 0 = never the flat plan (tests / tuning; size the workspace with the same hint) */
+    int32_t reserved0;    /* must be 0 */
     /* query / output: fp16 [B, Hq, 128] contiguous */
     const void* q;
     void* out;
@@ -204,12 +208,18 @@ typedef struct mfb200_decode_params {
  * counter_bytes) followed by the partials as 8-byte {fp32, tag} entries.
  * The WHOLE workspace must be zero before the first launch on it (and again if batch / kv_heads / groups change);
  * launches keep it consistent afterwards (tags only grow), so it is graph-replayable. */
-int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count,
+int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count, int plan_hint,
                        size_t* workspace_bytes, size_t* counter_bytes);
 /* Host-only self-check of the work decomposition the launch would use for this geometry: every unit's blocks covered
  * exactly once, per-CTA block limit, unique partial slots inside the workspace stride, merge ownership.  Returns
  * MFB200_OK or MFB200_EINVAL (mfb200_last_error() names the first inconsistency).  Needs no GPU when sm_count > 0. */
-int mfb200_decode_plan_check(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count);
+int mfb200_decode_plan_check(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count, int plan_hint);
+/* Scheduling assumption (short launches only): when every compressed CTA of a launch is resident at once and holds <= 16
+ * blocks, the split merge uses a "flagged" protocol in which the CTA with the HIGHEST index of a unit waits (bounded
+ * back-off polling of L2) for partials written by lower-indexed CTAs of the same launch.  This relies on the hardware
+ * dispatching the CTAs of a 1-D grid in ascending blockIdx order, which every CUDA GPU to date does but CUDA does not
+ * promise; under MPS time-slicing or a debugger that single-steps CTAs the wait can be long (never wrong).  All other
+ * launches use an atomic ticket (last arrival merges) and wait for nothing. */
 int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb200_stream_t stream);
 
 /* One decode step on a long-lived parameter block (the host keeps one per layer cache): sets q / out /
@@ -218,7 +228,14 @@ int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb200_stream_
  * Exists so that a per-layer decode step costs the host a single FFI call. */
 int mfb200_decode_step(mfb200_decode_params* p, const void* q, const void* k_new, const void* v_new, void* out,
                        int sm_count, mfb200_stream_t stream);
-/* Workspace size that is sufficient for every (comp_len <= max_comp_len, win_len <= max_win_len). */
+/* The same for a whole decoder: layer l uses layers[l] and q + l*q_layer_stride, k_new/v_new + l*kv_layer_stride,
+ * out + l*out_layer_stride (strides in halves).  One FFI call per decode step instead of one per layer; the launches are
+ * issued back to back on `stream`.  Returns n_layers, or the first error (layers before it were launched and advanced,
+ * the failing layer and the ones after it are untouched). */
+int mfb200_decode_step_layers(mfb200_decode_params* const* layers, int n_layers, const void* q, const void* k_new,
+                              const void* v_new, void* out, int64_t q_layer_stride, int64_t kv_layer_stride,
+                              int64_t out_layer_stride, mfb200_stream_t stream);
+/* Workspace size that is sufficient for every (comp_len <= max_comp_len, win_len <= max_win_len), plan_hint 0. */
 size_t mfb200_decode_workspace_max(int batch, int kv_heads, int groups, int max_comp_len, int max_win_len,
                                    int sm_count);
 

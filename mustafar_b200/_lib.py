@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MFB200_LIB", os.path.join(_HERE, "libmustafar_b200.so"))  # override: A/B builds only
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 LAYOUT_KEY = 0
 LAYOUT_VALUE = 1
 F_REF_SCORE_ROUNDING = 1
@@ -29,7 +29,7 @@ class DecodeParams(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("kv_heads", C.c_int32), ("groups", C.c_int32), ("comp_len", C.c_int32),
         ("win_len", C.c_int32), ("flags", C.c_int32), ("score_div", C.c_float), ("n_split", C.c_int32),
-        ("slot_kb", C.c_int32), ("workspace_kb", C.c_int32),
+        ("slot_kb", C.c_int32), ("workspace_kb", C.c_int32), ("plan_hint", C.c_int32), ("reserved0", C.c_int32),
         ("q", _vp), ("out", _vp),
         ("k_bmp", _vp), ("k_idx", _vp), ("k_nz", _vp), ("k_nz_off", _vp),
         ("v_bmp", _vp), ("v_idx", _vp), ("v_nz", _vp), ("v_nz_off", _vp),
@@ -56,10 +56,11 @@ SIGNATURES = {
     "mfb200_key_formulation": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32]),
     "mfb200_value_formulation": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32]),
     "mfb200_value_workspace_bytes": (C.c_size_t, [_i32, _i32]),
-    "mfb200_decode_plan": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
-    "mfb200_decode_plan_check": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "mfb200_decode_plan": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "mfb200_decode_plan_check": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "mfb200_sparse_decode_attention": (_i32, [C.POINTER(DecodeParams), _vp]),
     "mfb200_decode_step": (_i32, [C.POINTER(DecodeParams), _vp, _vp, _vp, _vp, _i32, _vp]),
+    "mfb200_decode_step_layers": (_i32, [C.POINTER(C.POINTER(DecodeParams)), _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "mfb200_decode_workspace_max": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "mfb200_window_append": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
 }

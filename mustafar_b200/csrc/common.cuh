@@ -37,6 +37,24 @@ int cuda_fail(cudaError_t e, const char* what);
         if (_e != cudaSuccess) return mfb::cuda_fail(_e, #expr);    \
     } while (0)
 
+// Per-device state.  cudaFuncSetAttribute and the SM count are properties of a DEVICE, not of the process: a host that
+// drives several GPUs from one process (e.g. HF device_map sharding, pred_long_bench.py:165) must configure every
+// kernel on every device it launches on.
+constexpr int kMaxDevices = 64;
+int current_device_sm_count(int* out);  // cached per device ordinal
+// Raises a kernel's dynamic shared-memory limit on the CURRENT device if this device has not seen `bytes` yet.
+// `cache` is one zero-initialised array per kernel instantiation; races only repeat an idempotent call.
+template <class Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, size_t (&cache)[kMaxDevices], size_t bytes) {
+    int dev = 0;
+    MFB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices || cache[dev] < bytes) {
+        MFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+        if (dev >= 0 && dev < kMaxDevices) cache[dev] = bytes;
+    }
+    return MFB200_OK;
+}
+
 inline int launch_status(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, what);
@@ -76,6 +94,14 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
 __device__ __forceinline__ uint2 ldg_stream_v2(const void* p) {
     uint2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+// the same without .nc: for memory the kernel itself writes later (the read-only path requires the data to stay
+// unmodified for the whole kernel)
+__device__ __forceinline__ uint2 ld_coherent_v2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
     return r;
 }
 

@@ -1017,11 +1017,10 @@ static int launch_decode(const DecodeArgs& a, cudaStream_t s) {
     const SmemMap sm = smem_map(G, a.slot_nz_bytes, a.depth);
     size_t smem = (a.n_csplit > 0 || a.n_extra > 0 || a.flat_ctas > 0) ? sm.total : 0;
     if (a.n_wsplit > 0) smem = smem > window_smem_bytes(G) ? smem : window_smem_bytes(G);
-    static size_t configured = 0;
-    if (smem > configured) {
-        MFB_CUDA(cudaFuncSetAttribute(sparse_decode_attn_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
-        configured = smem;
+    static size_t configured[kMaxDevices] = {0};  // per device, per instantiation
+    if (smem > 0) {
+        const int rc = ensure_dynamic_smem(sparse_decode_attn_kernel<G, MODE>, configured, smem);
+        if (rc) return rc;
     }
     cudaLaunchConfig_t cfg = {};
     const int units = a.p.batch * a.p.kv_heads;
@@ -1051,7 +1050,8 @@ struct Plan {
 //  * uniform mode: every unit is cut into the same number of compressed splits;
 //  * flat mode (24..256 blocks per CTA): the launch's units*nblk blocks are divided evenly over exactly the
 //    resident CTA slots, CTAs may cross unit boundaries -> no wave-quantisation loss for mid-size batches.
-static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count) {
+// plan_hint (mfb200_decode_params::plan_hint): 0 = automatic, n > 0 = flat plan with n compressed CTAs, < 0 = never flat.
+static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count, int plan_hint = 0) {
     Plan pl = {0, 0, (win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit, 0, 0, 0, 0, 0};
     const int64_t units = static_cast<int64_t>(batch) * kv_heads;
     const int nblk = comp_len / kBlockTokens;
@@ -1061,8 +1061,7 @@ static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win
         // the slots of the first compressed CTAs that finish (a reserve of up to slots/8 measured 2 % slower at batch 1).
         const int64_t avail = slots;
         const int64_t B = units * nblk;
-        // testing / tuning override (not API): MFB200_FLAT=0 never uses the flat mode, MFB200_FLAT=n forces n CTAs
-        static const int forced_flat = [] { const char* e = getenv("MFB200_FLAT"); return e ? atoi(e) : -1; }();
+        const int forced_flat = plan_hint > 0 ? plan_hint : (plan_hint < 0 ? 0 : -1);
         // flat mode: long CTAs need no reserve for the (short, trailing) window CTAs.  Large MHA launches get two
         // CTAs per slot (measured: 355 -> 320 us for 128 units x 508 blocks; the hardware scheduler evens out the tail).
         int64_t n_flat = 0;
@@ -1094,8 +1093,7 @@ static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win
             pl.max_split = (nblk + pl.flat_q - 1) / pl.flat_q + 1 + pl.n_wsplit;
             return pl;
         }
-        static const int forced_target = [] { const char* e = getenv("MFB200_TARGET_CTAS"); return e ? atoi(e) : 0; }();
-        const int64_t target = forced_target > 0 ? forced_target : avail;  // compressed CTAs of a uniform-mode launch
+        const int64_t target = avail;  // compressed CTAs of a uniform-mode launch
         int64_t per_unit = target / units;
         const int min_c = (nblk + kMaxBlocksPerSplit - 1) / kMaxBlocksPerSplit;
         if (per_unit < min_c) per_unit = min_c;
@@ -1109,35 +1107,21 @@ static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win
     pl.flagged = (nblk == 0 || (nblk + pl.n_csplit - 1) / pl.n_csplit <= 16) ? 1 : 0;
     return pl;
 }
-static int device_sm_count(int* out) {
-    static int cached[64] = {0};
-    int dev = 0;
-    MFB_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || cached[dev] == 0) {
-        int n = 0;
-        MFB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-        if (dev >= 0 && dev < 64) cached[dev] = n;
-        *out = n;
-    } else {
-        *out = cached[dev];
-    }
-    return MFB200_OK;
-}
 }  // namespace mfb
 
-extern "C" int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count,
+extern "C" int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count, int plan_hint,
                                   size_t* workspace_bytes, size_t* counter_bytes) {
     MFB_REQUIRE(batch > 0 && kv_heads > 0, "decode_plan: batch/kv_heads must be positive");
     MFB_REQUIRE(groups == 1 || groups == 2 || groups == 4 || groups == 8, "decode_plan: groups=%d not in {1,2,4,8}", groups);
     MFB_REQUIRE(comp_len >= 0 && comp_len % 64 == 0, "decode_plan: comp_len=%d must be a multiple of 64", comp_len);
     MFB_REQUIRE(win_len >= 0 && comp_len + win_len >= 1, "decode_plan: empty context");
     if (sm_count <= 0) {
-        const int rc = device_sm_count(&sm_count);
+        const int rc = current_device_sm_count(&sm_count);
         if (rc) return rc;
     }
     const int64_t units = static_cast<int64_t>(batch) * kv_heads;
     MFB_REQUIRE(units <= (1 << 20), "decode_plan: batch*kv_heads=%lld exceeds 2^20", static_cast<long long>(units));
-    const Plan pl = make_plan(batch, kv_heads, groups, comp_len, win_len, sm_count);
+    const Plan pl = make_plan(batch, kv_heads, groups, comp_len, win_len, sm_count, plan_hint);
     const size_t cbytes = 2 * ws_counter_bytes(static_cast<size_t>(units));
     if (counter_bytes) *counter_bytes = cbytes;
     if (workspace_bytes) *workspace_bytes = cbytes + static_cast<size_t>(units) * pl.max_split * groups * kPartStride * 8;
@@ -1148,12 +1132,12 @@ extern "C" int mfb200_decode_plan(int batch, int kv_heads, int groups, int comp_
 // (same helpers: flat_start / flat_owner / unit_csplits) and verifies that every unit's blocks are covered exactly
 // once, that no CTA exceeds the per-CTA block limit, that partial slots are unique and inside the workspace stride,
 // and that the flagged merge's owner of the last slot is the unit's highest CTA index.  No GPU involved.
-extern "C" int mfb200_decode_plan_check(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count) {
+extern "C" int mfb200_decode_plan_check(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count, int plan_hint) {
     size_t ws = 0;
-    const int rc = mfb200_decode_plan(batch, kv_heads, groups, comp_len, win_len, sm_count > 0 ? sm_count : 148, &ws, nullptr);
+    const int rc = mfb200_decode_plan(batch, kv_heads, groups, comp_len, win_len, sm_count > 0 ? sm_count : 148, plan_hint, &ws, nullptr);
     if (rc < 0) return rc;
     if (sm_count <= 0) sm_count = 148;
-    const Plan pl = make_plan(batch, kv_heads, groups, comp_len, win_len, sm_count);
+    const Plan pl = make_plan(batch, kv_heads, groups, comp_len, win_len, sm_count, plan_hint);
     DecodeArgs a = {};
     a.p.batch = batch;
     a.p.kv_heads = kv_heads;
@@ -1283,10 +1267,10 @@ extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb
     a.p = *p;
     int sm_count = 0;
     {
-        const int rc = device_sm_count(&sm_count);
+        const int rc = current_device_sm_count(&sm_count);
         if (rc) return rc;
     }
-    const Plan pl = make_plan(p->batch, p->kv_heads, p->groups, p->comp_len, p->win_len, sm_count);
+    const Plan pl = make_plan(p->batch, p->kv_heads, p->groups, p->comp_len, p->win_len, sm_count, p->plan_hint);
     a.n_csplit = pl.n_csplit;
     a.n_extra = pl.n_extra;
     a.n_wsplit = pl.n_wsplit;
@@ -1317,7 +1301,7 @@ extern "C" size_t mfb200_decode_workspace_max(int batch, int kv_heads, int group
     // The number of partial slots per unit is not monotone in the lengths (ragged splits, the switch between the
     // uniform and the flat plan, k-wave flat plans): take the maximum over EVERY (compressed length, window chunk
     // count) the cache can pass through.  Pure host arithmetic, a few microseconds per thousand tokens of capacity.
-    if (sm_count <= 0 && device_sm_count(&sm_count) != MFB200_OK) sm_count = 148;
+    if (sm_count <= 0 && current_device_sm_count(&sm_count) != MFB200_OK) sm_count = 148;
     size_t best = 0;
     const int max_nw = (max_win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit;
     for (int comp = 0; comp <= max_comp_len - max_comp_len % kBlockTokens; comp += kBlockTokens) {
@@ -1325,7 +1309,7 @@ extern "C" size_t mfb200_decode_workspace_max(int batch, int kv_heads, int group
             int win = nw * kWinTokensPerSplit;
             if (win > max_win_len) win = max_win_len > 0 ? max_win_len : 1;
             size_t ws = 0;
-            if (mfb200_decode_plan(batch, kv_heads, groups, comp, win, sm_count, &ws, nullptr) > 0 && ws > best) best = ws;
+            if (mfb200_decode_plan(batch, kv_heads, groups, comp, win, sm_count, 0, &ws, nullptr) > 0 && ws > best) best = ws;
         }
     }
     return best + 4096;
@@ -1340,7 +1324,24 @@ extern "C" int mfb200_decode_step(mfb200_decode_params* p, const void* q, const 
     p->v_new = v_new;
     (void)sm_count;
     p->win_len += 1;
-    return mfb200_sparse_decode_attention(p, stream);
+    const int rc = mfb200_sparse_decode_attention(p, stream);
+    if (rc < 0) p->win_len -= 1;  // nothing was launched: the long-lived block keeps describing the cache as it is
+    return rc;
+}
+
+extern "C" int mfb200_decode_step_layers(mfb200_decode_params* const* layers, int n_layers, const void* q, const void* k_new,
+                                         const void* v_new, void* out, int64_t q_layer_stride, int64_t kv_layer_stride,
+                                         int64_t out_layer_stride, mfb200_stream_t stream) {
+    MFB_REQUIRE(layers != nullptr && n_layers >= 0 && q && k_new && v_new && out, "decode_step_layers: null pointer");
+    for (int l = 0; l < n_layers; ++l) {
+        MFB_REQUIRE(layers[l] != nullptr, "decode_step_layers: layer %d has no parameter block", l);
+        const int rc = mfb200_decode_step(layers[l], static_cast<const __half*>(q) + l * q_layer_stride,
+                                          static_cast<const __half*>(k_new) + l * kv_layer_stride,
+                                          static_cast<const __half*>(v_new) + l * kv_layer_stride,
+                                          static_cast<__half*>(out) + l * out_layer_stride, 0, stream);
+        if (rc < 0) return rc;  // layers [0, l) were launched and advanced, layers [l, n) are untouched
+    }
+    return n_layers;
 }
 
 #ifdef MFB_TRACE

@@ -256,10 +256,11 @@ __device__ __forceinline__ void compress_chunk_body(const ChunkArgs& a, int whic
     __half* win = a.win[which] + h * a.win_stride;
     // 1. load + prune: warp w owns rows 8w .. 8w+7
     {
+        // coherent loads (not ld.global.nc): the same kernel overwrites these window rows in step 5
         const uint2* src = reinterpret_cast<const uint2*>(win);
         uint2 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = ldg_stream_v2(src + (warp * 8 + i) * 32 + lane);
+        for (int i = 0; i < 8; ++i) v[i] = ld_coherent_v2(src + (warp * 8 + i) * 32 + lane);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             v[i] = prune4(v[i], a.prune_k[which]);
@@ -369,8 +370,9 @@ constexpr size_t kChunkSmem = kChunkTokens * kPitch * 2 + 3 * kChunkTiles * 4 + 
 // is the sum of the padded counts of all earlier blocks of the unit; instead of a count pass + scan pass + a
 // second read of the input, blocks exchange that sum with a decoupled look-back (Merrill & Garland): each CTA
 // publishes its aggregate as soon as it is known, then warp 0 walks back over the predecessors' status words
-// (32 per probe) until it meets an inclusive prefix.  Predecessors have smaller linear CTA indices, so they
-// were dispatched earlier and are either finished or running: the wait cannot deadlock.
+// (32 per probe) until it meets an inclusive prefix.  A CTA's logical block index is a TICKET drawn from a
+// per-(unit, K|V) atomic counter, not blockIdx.x: whoever holds ticket t knows that tickets < t were drawn by CTAs
+// that are already running or finished, so the wait cannot deadlock whatever order the hardware dispatches CTAs in.
 // Algorithmic bytes per token-head and stream: 256 read + 16 bitmap + 8 idx + the padded nonzeros written.
 struct PrefillArgs {
     const __half* x[2];                   // key_states, value_states: [B, Hkv, tokens, 128], innermost stride 1
@@ -384,6 +386,7 @@ struct PrefillArgs {
     int64_t bmp_stride, idx_stride, tile_offset, head_capacity;
     int32_t* overflow;
     unsigned long long* status;           // [2][units][blocks], zeroed by the host: (state << 32) | value
+    unsigned int* ticket;                 // [2][units], zeroed by the host: next logical block of the chain
 };
 constexpr unsigned long long kStAggregate = 1ull << 32, kStPrefix = 2ull << 32;
 
@@ -428,8 +431,11 @@ __device__ __forceinline__ void prefill_block_body(const PrefillArgs& a, int whi
                                                    uint16_t (*stage)[16][64]) {
     __shared__ int32_t warp_tot[8];
     __shared__ int32_t s_excl;
-    const int tb = blockIdx.x;
+    __shared__ int s_tb;
     const int64_t u = blockIdx.y, units = gridDim.y, nblk = gridDim.x;
+    if (threadIdx.x == 0) s_tb = static_cast<int>(atomicAdd(&a.ticket[static_cast<int64_t>(which) * units + u], 1u));
+    __syncthreads();
+    const int tb = s_tb;
     const uint32_t lane = lane_id();
     const int warp = threadIdx.x >> 5;
     // 1. load + prune: warp w owns token rows 8w .. 8w+7 of the block
@@ -640,11 +646,10 @@ extern "C" int mfb200_compress_append_chunk(void* k_win, void* v_win, int64_t wi
                 "compress_append_chunk: cache slab too small for tile_offset=%lld", static_cast<long long>(tile_offset));
     MFB_REQUIRE(units >= 0 && units <= (1 << 20), "compress_append_chunk: units out of range");
     if (units == 0) return MFB200_OK;
-    static bool configured = false;
-    if (!configured) {
-        MFB_CUDA(cudaFuncSetAttribute(compress_append_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(kChunkSmem)));
-        configured = true;
+    static size_t configured[kMaxDevices] = {0};
+    {
+        const int rc = ensure_dynamic_smem(compress_append_chunk_kernel, configured, kChunkSmem);
+        if (rc) return rc;
     }
     ChunkArgs a;
     a.win[0] = static_cast<__half*>(k_win);
@@ -694,7 +699,7 @@ extern "C" int mfb200_compress_prefill(const void* k, const void* v, const int64
     const int64_t units = static_cast<int64_t>(batch) * kv_heads, nblk = tokens / 64;
     if (units == 0 || nblk == 0) return MFB200_OK;
     auto s = static_cast<cudaStream_t>(stream);
-    MFB_CUDA(cudaMemsetAsync(status_ws, 0, static_cast<size_t>(2 * units * nblk) * sizeof(unsigned long long), s));
+    MFB_CUDA(cudaMemsetAsync(status_ws, 0, static_cast<size_t>(2 * units * nblk + 2 * units) * sizeof(unsigned long long), s));
     PrefillArgs a;
     a.x[0] = static_cast<const __half*>(k);
     a.x[1] = static_cast<const __half*>(v);
@@ -721,6 +726,7 @@ extern "C" int mfb200_compress_prefill(const void* k, const void* v, const int64
     a.head_capacity = head_capacity;
     a.overflow = overflow;
     a.status = static_cast<unsigned long long*>(status_ws);
+    a.ticket = reinterpret_cast<unsigned int*>(a.status + 2 * units * nblk);
     dim3 grid(static_cast<unsigned>(nblk), static_cast<unsigned>(units), 2);
     compress_prefill_kernel<<<grid, kCompressThreads, 0, s>>>(a);
     return launch_status("compress_prefill_kernel");

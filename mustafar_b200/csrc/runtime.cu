@@ -20,6 +20,21 @@ int cuda_fail(cudaError_t e, const char* what) {
     return MFB200_ECUDA;
 }
 
+int current_device_sm_count(int* out) {
+    static int cached[kMaxDevices] = {0};
+    int dev = 0;
+    MFB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices || cached[dev] == 0) {
+        int n = 0;
+        MFB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < kMaxDevices) cached[dev] = n;
+        *out = n;
+    } else {
+        *out = cached[dev];
+    }
+    return MFB200_OK;
+}
+
 }  // namespace mfb
 
 extern "C" int mfb200_abi_version(void) { return MFB200_ABI_VERSION; }

@@ -197,7 +197,9 @@ value_formulation_kernel(const uint64_t* __restrict__ bmp, const uint8_t* __rest
 
 static int value_n_split(int L, int batch) {
     const int nblk = L / 64;
-    int ns = (148 * 4 + batch - 1) / batch;
+    int sms = 0;
+    if (current_device_sm_count(&sms) != MFB200_OK || sms <= 0) sms = 148;  // no device (host-only sizing call): B200
+    int ns = (sms * 4 + batch - 1) / batch;
     if (ns > 32) ns = 32;
     if (ns > nblk) ns = nblk;
     if (ns < 1) ns = 1;

@@ -25,6 +25,7 @@ There is no CPU fallback: the cache and the decode path need the CUDA library.
 from __future__ import annotations
 
 import math
+import threading
 from typing import Optional
 
 import torch
@@ -35,6 +36,11 @@ from transformers.masking_utils import sdpa_mask
 from .attention import HEAD_DIM, MustafarKVCache
 
 ATTN_NAME = "mustafar"
+
+# The attention-interface function receives the attention MODULE (with its `layer_idx`) but not `past_key_values`.
+# `Cache.update` runs in the same module forward immediately before it, so the cache that was updated last on this
+# thread is the one the attention call belongs to.
+_ACTIVE = threading.local()
 
 
 class MustafarLayer(CacheLayerMixin):
@@ -68,7 +74,6 @@ class MustafarLayer(CacheLayerMixin):
             raise NotImplementedError("MustafarCache: multi-token continuation (chunked prefill) is not supported; "
                                       "the reference supports a single prefill followed by 1-token decode steps")
         self.seen_tokens += n
-        key_states._mustafar_layer = self  # the attention function receives this very tensor object
         return key_states, value_states
 
     def get_seq_length(self) -> int:
@@ -111,12 +116,22 @@ class MustafarCache(Cache):
         super().__init__(layers=[MustafarLayer(groups, k_sparsity, v_sparsity, residual_length, max_tokens)
                                  for _ in range(text.num_hidden_layers)])
 
+    def update(self, key_states, value_states, layer_idx, *args, **kwargs):
+        _ACTIVE.cache = self  # consumed by mustafar_attention_forward through module.layer_idx
+        return super().update(key_states, value_states, layer_idx, *args, **kwargs)
+
+    def bytes_held(self) -> int:
+        """Device bytes of all layer caches (the reference reports torch.cuda.max_memory_allocated, mem_spd_test.py:95)."""
+        return sum(l.kv.bytes_held() for l in self.layers if l.kv is not None)
+
 
 def mustafar_attention_forward(module, query, key, value, attention_mask, scaling=None, dropout=0.0, **kwargs):
     """transformers attention-interface function; see the module docstring.  Returns ([B, q_len, Hq, 128], None)."""
-    layer: Optional[MustafarLayer] = getattr(key, "_mustafar_layer", None)
-    if layer is None:
+    cache: Optional[MustafarCache] = getattr(_ACTIVE, "cache", None)
+    idx = getattr(module, "layer_idx", None)
+    if cache is None or idx is None or idx >= len(cache.layers) or not cache.layers[idx].is_initialized:
         raise RuntimeError('attn_implementation="mustafar" needs past_key_values=MustafarCache(config, ...)')
+    layer: MustafarLayer = cache.layers[idx]
     if dropout:
         raise RuntimeError("mustafar attention: dropout is not supported (inference path)")
     b, hq, q_len, d = query.shape
@@ -132,8 +147,13 @@ def mustafar_attention_forward(module, query, key, value, attention_mask, scalin
     mask = None
     if attention_mask is not None:  # [B, 1, 1, kv_len]: bool (True = attend) or additive
         if attention_mask.dtype == torch.bool:
-            mask = torch.zeros(attention_mask.shape, dtype=torch.float16, device=query.device)
-            mask.masked_fill_(~attention_mask, float("-inf"))
+            # one additive mask per decode step, shared by all layers (the model hands every layer the same tensor)
+            memo = getattr(_ACTIVE, "mask_memo", None)
+            if memo is None or memo[0] is not attention_mask:
+                add = torch.zeros(attention_mask.shape, dtype=torch.float16, device=query.device)
+                add.masked_fill_(~attention_mask, float("-inf"))
+                memo = _ACTIVE.mask_memo = (attention_mask, add)
+            mask = memo[1]
         else:
             mask = attention_mask
     out = layer.kv.decode_step(query, key, value, mask)  # [B, Hq, 1, 128]

@@ -65,6 +65,8 @@ def mustafar_value_formulation(bmp, NZ, idx, NZ_Offset, B, Reduction_Workspace, 
         key = (B.device.index, torch.cuda.current_stream().cuda_stream)
         ws = _value_ws.get(key)
         if ws is None or ws.numel() < nbytes:
+            if len(_value_ws) >= 16:  # bounded: drop the workspaces of streams that are no longer in use
+                _value_ws.clear()
             ws = torch.zeros((nbytes,), dtype=torch.uint8, device=B.device)
             _value_ws[key] = ws
         C = torch.empty((Batch_Size, 8, M_Global), dtype=torch.float16, device=B.device)

@@ -27,14 +27,14 @@ def test_every_declared_symbol_is_exported(lib):
     for name in declared:
         assert hasattr(raw, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
-    assert lib.mfb200_abi_version() == 1
+    assert lib.mfb200_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
     from mustafar_b200 import _lib
-    # 10 x int32/float, then 8-byte fields only
-    assert _lib.DecodeParams.q.offset == 40
-    assert C.sizeof(_lib.DecodeParams) == 40 + 20 * 8
+    # 12 x int32/float, then 8-byte fields only
+    assert _lib.DecodeParams.q.offset == 48
+    assert C.sizeof(_lib.DecodeParams) == 48 + 20 * 8
 
 
 def test_argument_validation_without_gpu(lib):
@@ -47,10 +47,10 @@ def test_argument_validation_without_gpu(lib):
                                       C.c_void_p(16), C.c_void_p(16), 256, 4, 128, None, 1, 2, 1) == -1
     assert b"N_Global" in lib.mfb200_last_error()
     ws, cb = C.c_size_t(0), C.c_size_t(0)
-    n = lib.mfb200_decode_plan(1, 32, 1, 3840, 256, 148, C.byref(ws), C.byref(cb))
+    n = lib.mfb200_decode_plan(1, 32, 1, 3840, 256, 148, 0, C.byref(ws), C.byref(cb))
     assert n >= 2 and ws.value > cb.value > 0
-    assert lib.mfb200_decode_plan(1, 32, 3, 3840, 256, 148, C.byref(ws), C.byref(cb)) == -1
-    assert lib.mfb200_decode_plan(1, 32, 1, 3841, 256, 148, C.byref(ws), C.byref(cb)) == -1
+    assert lib.mfb200_decode_plan(1, 32, 3, 3840, 256, 148, 0, C.byref(ws), C.byref(cb)) == -1
+    assert lib.mfb200_decode_plan(1, 32, 1, 3841, 256, 148, 0, C.byref(ws), C.byref(cb)) == -1
     p = _lib.DecodeParams()
     assert lib.mfb200_sparse_decode_attention(C.byref(p), None) == -1
 
@@ -89,7 +89,7 @@ def test_workspace_max_covers_every_shorter_context(lib):
                     if comp == 0 and win == 0:
                         continue
                     ws, cb = C.c_size_t(0), C.c_size_t(0)
-                    n = lib.mfb200_decode_plan(batch, hkv, g, comp, win, 148, C.byref(ws), C.byref(cb))
+                    n = lib.mfb200_decode_plan(batch, hkv, g, comp, win, 148, 0, C.byref(ws), C.byref(cb))
                     assert n >= 1, (batch, hkv, g, comp, win)
                     assert ws.value <= ws_max, (batch, hkv, g, comp, win, ws.value, ws_max)
                     assert cb.value >= 2 * 4 * batch * hkv and cb.value % 256 == 0
@@ -107,8 +107,13 @@ def test_plan_self_check_over_geometries(lib):
                 for win in (0, 1, 64, 65, 288):
                     if comp == 0 and win == 0:
                         continue
-                    rc = lib.mfb200_decode_plan_check(batch, hkv, g, comp, win, sm)
+                    rc = lib.mfb200_decode_plan_check(batch, hkv, g, comp, win, sm, 0)
                     assert rc == 0, (sm, batch, hkv, g, comp, win, lib.mfb200_last_error())
                     n += 1
     assert n > 10000
-    assert lib.mfb200_decode_plan_check(1, 32, 3, 4096, 64, 148) < 0  # invalid geometry is an error, not a crash
+    assert lib.mfb200_decode_plan_check(1, 32, 3, 4096, 64, 148, 0) < 0  # invalid geometry is an error, not a crash
+    # forced plans (mfb200_decode_params::plan_hint): flat with n CTAs on shapes that would not choose it, and never-flat
+    for hint in (5, 12, 37, 300, -1):
+        for batch, hkv, g, comp in [(1, 8, 1, 2048), (1, 4, 4, 1280), (2, 4, 2, 1024), (1, 8, 8, 1024), (8, 16, 1, 4096)]:
+            rc = lib.mfb200_decode_plan_check(batch, hkv, g, comp, 64, 148, hint)
+            assert rc == 0, (hint, batch, hkv, g, comp, lib.mfb200_last_error())

@@ -428,13 +428,21 @@ def test_launch_refuses_a_workspace_that_is_too_small():
 
 
 def test_slab_overflow_is_detected_not_corrupting():
-    from mustafar_b200.attention import MustafarKVCache
-    b, hkv = 1, 2
-    cache = MustafarKVCache(b, hkv, 1, max_tokens=512, k_sparsity=0.5, v_sparsity=0.5, nz_halves_per_token=32)
-    k = _randn((b, hkv, 300, 128), 1).cuda()
-    cache.prefill(k, k)
-    with pytest.raises(RuntimeError):
-        cache.check_overflow()
+    """C-ABI level guard (callers that manage their own slabs): a tile that does not fit its slab is not written and the
+    device flag is raised.  (MustafarKVCache never gets there: tests/test_gpu_configs.py::test_slabs_regrow_...)"""
+    from mustafar_b200 import _lib, compression
+    x = _randn((2, 256, 128), 1).cuda()
+    bitmaps = torch.empty((2, 512), dtype=torch.int64, device="cuda")
+    counts = torch.empty((2, 512), dtype=torch.int32, device="cuda")
+    accum = torch.empty((2, 513), dtype=torch.int32, device="cuda")
+    compression.compress_into(x, _lib.LAYOUT_VALUE, 64, bitmaps, counts, accum, 513, 0, None)
+    cap = 4096  # halves per head: far less than the ~18K the chunk needs
+    packed = torch.full((2 * cap + 64,), 7.0, dtype=torch.float16, device="cuda")
+    overflow = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    base = torch.tensor([0, cap], dtype=torch.int64, device="cuda")
+    compression.pack_into(x, _lib.LAYOUT_VALUE, bitmaps, accum, 513, 0, base, packed, cap, overflow)
+    assert int(overflow.item()) == 1
+    assert torch.all(packed[2 * cap:] == 7.0)  # nothing was written past the second head's slab
 
 
 @pytest.mark.parametrize("b,hkv,groups,T,sparsity", [(4, 8, 4, 8192, 0.7), (2, 8, 8, 4160, 0.5), (1, 8, 4, 8192, 0.5),
@@ -492,8 +500,8 @@ def test_decode_launches_replay_in_a_cuda_graph():
 
 def test_flat_partition_mode():
     """Mid-size launches use the flat work partition (all blocks of all units divided evenly over the resident
-    CTA slots; CTAs cross unit boundaries and process several segments).  Forced here on small shapes through the
-    MFB200_FLAT tuning override, plus one shape that selects it naturally; checked against the masked-dense oracle."""
+    CTA slots; CTAs cross unit boundaries and process several segments).  Forced here on small shapes through
+    mfb200_decode_params::plan_hint, plus one shape that selects it naturally; checked against the masked-dense oracle."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -506,7 +514,7 @@ for (b, hkv, g, T, s) in SHAPES:
     gen = torch.Generator().manual_seed(T + g)
     k = torch.randn(b, hkv, T, 128, generator=gen).half(); v = torch.randn(b, hkv, T, 128, generator=gen).half()
     q = torch.randn(b, hkv * g, 1, 128, generator=gen).half()
-    c = MustafarKVCache(b, hkv, g, T + 64, s, s); c.prefill(k.cuda(), v.cuda())
+    c = MustafarKVCache(b, hkv, g, T + 64, s, s, plan_hint=HINT); c.prefill(k.cuda(), v.cuda())
     outs = [c.attend(q.cuda()).clone() for _ in range(3)]
     torch.cuda.synchronize()
     assert all(torch.equal(outs[0], o) for o in outs[1:])
@@ -520,11 +528,7 @@ print("FLAT-OK")
     cases = [("5", "[(1, 8, 1, 2112, 0.5), (1, 4, 4, 1312, 0.7)]"), ("12", "[(1, 8, 1, 2112, 0.5), (2, 4, 2, 1088, 0.5)]"),
              ("37", "[(1, 8, 4, 2112, 0.7), (1, 8, 8, 1088, 0.5)]"), (None, "[(8, 16, 1, 4160, 0.7)]")]
     for forced, shapes in cases:
-        env = dict(os.environ)
-        env.pop("MFB200_FLAT", None)
-        if forced is not None:
-            env["MFB200_FLAT"] = forced
-        r = subprocess.run([sys.executable, "-c", "SHAPES = " + shapes + code], env=env, capture_output=True, text=True, timeout=300)
+        r = subprocess.run([sys.executable, "-c", "HINT = %s\nSHAPES = " % (forced or "0") + shapes + code], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "FLAT-OK" in r.stdout, (forced, r.stdout[-1500:] + r.stderr[-1500:])
 
 
