@@ -227,7 +227,7 @@ class MustafarKVCache:
             prune_rank(self.v_sparsity), sk.bmp[unit0:].data_ptr(), sk.idx[unit0:].data_ptr(), sk.nz.data_ptr(),
             sk.head_base[unit0:].data_ptr(), sv.bmp[unit0:].data_ptr(), sv.idx[unit0:].data_ptr(), sv.nz.data_ptr(),
             sv.head_base[unit0:].data_ptr(), sk.cap_tiles, sk.cap_tiles + 1,
-            0, min(sk.head_capacity, sv.head_capacity), self.overflow.data_ptr(), self._prefill_status.data_ptr(),
+            self.comp_len * 2, min(sk.head_capacity, sv.head_capacity), self.overflow.data_ptr(), self._prefill_status.data_ptr(),
             _lib.stream_ptr()), "mfb200_compress_prefill")
 
     def prefill(self, key_states: torch.Tensor, value_states: torch.Tensor, batch_start: int = 0):
@@ -240,6 +240,7 @@ class MustafarKVCache:
         assert (h, d) == (self.kv_heads, HEAD_DIM) and t <= self.cap_tokens and batch_start + b <= self.batch
         L = compressed_length(t, self.residual_length)
         u0, u1 = batch_start * h, (batch_start + b) * h
+        self.comp_len = 0  # the prompt is compressed from tile 0
         with torch.cuda.device(self.device):
             if L > 0:
                 self._compress_prompt(key_states, value_states, L, u0)
