@@ -143,10 +143,11 @@ class MustafarKVCache:
         self._step = None
         self._sm_count = 0
         self._attn = _lib.load().mfb200_sparse_decode_attention
-        # staging capacity for one 64-token block of nonzeros: kept + pad + slack for ties, in KB
+        # staging capacity for one 64-token block of nonzeros, in KB: survivors + the expected tile padding (7 halves per
+        # token) + 2 halves per token for ties; the rare block that is larger takes the kernel's slower global-load path
         def slot_kb(s):
             kept = HEAD_DIM - prune_rank(s) + 1
-            return min(16, max(1, math.ceil(64 * (kept + 8 + 8) * 2 / 1024)))
+            return min(16, max(1, math.ceil(64 * (kept + 7 + 2) * 2 / 1024)))
         self.slot_kb = max(slot_kb(k_sparsity), slot_kb(v_sparsity))
 
     # ------------------------------------------------------------------ properties

@@ -27,8 +27,15 @@
 // dense buffer on the tensor cores (gqa_mma.cuh).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "gqa_mma.cuh"
+#include "gqa_tc.cuh"
 #include "sparse_tile.cuh"
+
+#ifndef MFB_GQA_TC
+#define MFB_GQA_TC 1  // 1: G >= 4 contracts on tcgen05 (gqa_tc.cuh); 0: the round-1 mma.sync path (gqa_mma.cuh), kept for A/B runs
+#endif
 
 namespace mfb {
 
@@ -38,12 +45,20 @@ namespace mfb {
 constexpr int kTileWarps = 4;                 // per role
 constexpr int kWarpV0 = 4, kWarpSoftmax = 8, kWarpProducer = 9;  // warps 0-3: K role
 constexpr int kAttnWarps = 10;
-constexpr int kAttnThreads = kAttnWarps * 32;  // 320
+constexpr int kAttnThreads = kAttnWarps * 32;  // 320: CUDA-core variant (G <= 2)
+// tcgen05 variant (G >= 4): warps 0-3 K decode, 4-7 V decode, 8-11 softmax / epilogue (TMEM lane quadrant = warp % 4),
+// 12 producer (+ TMEM alloc), 13 issues the score MMAs, 14 the output MMAs
+constexpr int kTcWarps = 15;
+constexpr int kTcThreads = kTcWarps * 32;  // 480
+constexpr int kWarpEpi0 = 8, kWarpProducerTc = 12, kWarpMmaS = 13, kWarpMmaO = 14;
+constexpr bool use_tc(int G) { return MFB_GQA_TC != 0 && G >= 4; }
+constexpr int cta_threads(int G) { return use_tc(G) ? kTcThreads : kAttnThreads; }
 constexpr int kWinWarps = 8;                   // warps used by the dense-window path
 constexpr int kWinThreads = kWinWarps * 32;
 constexpr int kChunk = 16;                     // tiles per operand-register chunk
 constexpr int kMaxDepth = 4;
 constexpr int kMaxBlocksPerSplit = 128;
+constexpr int kMaxBlocksPerSplitTc = 64;  // tcgen05 variant: smaller segment tables (shared memory goes to the dense operand buffers)
 constexpr int kWinTokensPerSplit = 64;
 constexpr int kPartStride = 132;  // {fp32 value, tag} entries per (split, head): o[128], m, l, pad
 constexpr float kLog2e = 1.4426950408889634f;
@@ -60,6 +75,7 @@ struct DecodeArgs {
     int flagged;    // split-merge protocol: 1 = flagged partials + designated merger, 0 = ticket (see publish_or_merge)
     int slot_nz_bytes;  // capacity of a slot's nonzero area (multiple of 1024)
     int depth;          // ring depth per stream (K and V each), 2..4
+    int nvd;            // tcgen05 variant: dense V buffers (1 or 2; K always has 2)
 };
 
 // barrier indices inside the bars[] array
@@ -157,6 +173,29 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {  // whole war
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ex2.approx: what exp2f() uses minus its denormal-range fix-up (results below 2^-126 flush to 0; p is rounded to fp16 anyway)
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// x / d as q0 = x * r, q = q0 + (x - q0 * d) * r with r = 1/d (one Newton correction on the quotient): the fast path of the
+// IEEE division routine without its call, range checks and slow path (about 30 instructions per score).  Correctly rounded
+// for the operand ranges here (fp16-valued x, d = sqrt(head_dim)) up to rare last-bit cases that vanish in the fp16
+// rounding that follows.
+__device__ __forceinline__ float div_fast(float x, float d, float r) {
+    const float q0 = x * r;
+    return fmaf(fmaf(-q0, d, x), r, q0);
+}
+// same as ref_round_score below, with the division done by div_fast (rdiv = 1 / div)
+__device__ __forceinline__ float ref_round_score_fast(float dot, float div, float rdiv, bool ref_rounding) {
+    if (ref_rounding) {
+        const float s16 = __half2float(__float2half_rn(dot));
+        return __half2float(__float2half_rn(div_fast(s16, div, rdiv)));
+    }
+    return dot * rdiv;
 }
 
 __device__ __forceinline__ float ref_round_score(float dot, float div, bool ref_rounding) {
@@ -276,7 +315,7 @@ __device__ __forceinline__ void merge_unit(const DecodeArgs& a, int unit, int sp
         if (__syncthreads_and(ok)) break;  // also publishes s_red
         __nanosleep(backoff);              // some contributor has not landed yet (stale tags): look again
     }
-    for (int i = tid; i < G * 128; i += kAttnThreads) {
+    for (int i = tid; i < G * 128; i += blockDim.x) {
         const int g = i >> 7, c = i & 127;
         float mx = -INFINITY;
 #pragma unroll
@@ -311,7 +350,7 @@ __device__ __forceinline__ void publish_or_merge(const DecodeArgs& a, int unit, 
         return;
     }
     uint2* mine = partial_ptr(a, G, unit, split);
-    for (int i = tid; i < G * 128; i += kAttnThreads)
+    for (int i = tid; i < G * 128; i += blockDim.x)
         mine[(i >> 7) * kPartStride + (i & 127)] = make_uint2(__float_as_uint(ored[i]), tag);
     if (tid < G) {
         mine[tid * kPartStride + 128] = make_uint2(__float_as_uint(m[tid]), tag);
@@ -427,7 +466,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     {
         const uint32_t* ki = p.k_idx + static_cast<int64_t>(unit) * p.idx_stride + static_cast<int64_t>(blk0) * 128;
         const uint32_t* vi = p.v_idx + static_cast<int64_t>(unit) * p.idx_stride + static_cast<int64_t>(blk0) * 128;
-        for (int i = tid; i <= nb * 4; i += kAttnThreads) {
+        for (int i = tid; i <= nb * 4; i += blockDim.x) {
             segk[i] = __ldg(ki + i * 32);
             segv[i] = __ldg(vi + i * 32);
         }
@@ -484,7 +523,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     }
     {
         const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
-        for (int i = tid; i < G * kHeadDim; i += kAttnThreads) qs[(i & 127) * G + (i >> 7)] = q[i];
+        for (int i = tid; i < G * kHeadDim; i += blockDim.x) qs[(i & 127) * G + (i >> 7)] = q[i];
     }
     __syncthreads();  // q staged (threads of every warp contribute) before the K warps read it
     if (tid == 0) {
@@ -733,13 +772,407 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         }
     }
     __syncthreads();
-    for (int i = tid; i < G * 128; i += kAttnThreads) {
+    for (int i = tid; i < G * 128; i += blockDim.x) {
         const int g = i >> 7, c = i & 127, hf = c >> 6, e = c & 63;
         ored[i] = red[((2 * hf) * G + g) * 64 + e] + red[((2 * hf + 1) * G + g) * 64 + e];
     }
     __syncthreads();
     publish_or_merge<G, FLAGGED>(a, unit, split, n_split, reinterpret_cast<const uint32_t*>(stat)[16], ored, stat, stat + 8,
                         reinterpret_cast<float*>(smem + sm.slots_v));
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 variant of the compressed split (G >= 4), see gqa_tc.cuh.  Pipeline per 64-token block n:
+//   producer --TMA--> ring slot --K decode warps--> Kd[n&1] --MMA-S--> S[n&1] (TMEM) --epilogue: softmax--> p[n&1]
+//                               --V decode warps--> Vd      ---------------------------MMA-O(p, Vd)--> O[n&1] (TMEM)
+//                                                                                      --epilogue: o = o*corr + O
+// The decode warps never wait for the softmax: K runs up to two blocks ahead (two dense K buffers), V one or two.
+// Hand-offs: everything a WARP signals goes through hardware named barriers (a warp parked in bar.sync issues nothing;
+// mbarrier sleepers are woken by every mbarrier event of the CTA and re-poll - the first version spent 10 of its 29
+// instructions per tile polling); what the TENSOR CORE signals (tcgen05.commit) has to be an mbarrier, and of the four
+// epilogue warps only warp 0 waits on those, the others follow through the epilogue's own named barrier.
+struct TcBars {
+    enum : int {
+        kFullK = 0, kFullV = kMaxDepth,  // [depth] TMA tx -> decode warps
+        kKdEmpty = 2 * kMaxDepth,        // [2] commit(MMA-S) -> K decode warps
+        kVdEmpty = kKdEmpty + 2,         // [2] commit(MMA-O) -> V decode warps
+        kSFull = kVdEmpty + 2,           // [2] commit(MMA-S) -> epilogue
+        kPEmpty = kSFull + 2,            // [2] commit(MMA-O) -> epilogue
+        kOFull = kPEmpty + 2,            // [2] commit(MMA-O) -> epilogue
+        kSEmpty = kOFull + 2,            // [2] epilogue (1 arrival) -> MMA-S
+        kOEmpty = kSEmpty + 2,           // [2] epilogue (1 arrival) -> MMA-O
+        kCount = kOEmpty + 2
+    };
+};
+// named barrier ids of the tcgen05 variant (ring depth 2): 0 __syncthreads, 5-6 kEmptyK, 9-10 kEmptyV (NamedBars), and
+struct TcNamed {
+    enum : int {
+        kKdFull = 1,   // [2] K decode warps arrive, MMA-S warp syncs
+        kVdFull = 3,   // [2] V decode warps arrive, MMA-O warp syncs
+        kPFull = 7,    // [2] epilogue warps arrive, MMA-O warp syncs
+        kEpi = 13,     // the four epilogue warps
+    };
+};
+struct TcSmemMap {
+    uint32_t slots_k, slots_v, kd, vd, qb, pb, bars, rec, segk, segv, wred, stat, total;
+};
+__host__ __device__ inline TcSmemMap tc_smem_map(int slot_nz_bytes, int depth, int nvd) {
+    TcSmemMap m;
+    uint32_t o = 0;
+    m.slots_k = o;
+    o += depth * (1024 + slot_nz_bytes);
+    m.slots_v = o;
+    o += depth * (1024 + slot_nz_bytes);
+    m.kd = o;
+    o += 2 * kDenseBytes;
+    m.vd = o;
+    o += nvd * kDenseBytes;
+    m.qb = o;
+    o += kQbBytes;
+    m.pb = o;
+    o += 2 * kPbBytes;
+    m.bars = o;
+    o += ((TcBars::kCount * 8 + 15) / 16) * 16;
+    m.rec = o;  // uint2 [8 decode warps][32 tiles][2]
+    o += 2 * kTileWarps * 64 * 8;
+    m.segk = o;
+    o += (kMaxBlocksPerSplitTc * 4 + 4) * 4;
+    m.segv = o;
+    o += (kMaxBlocksPerSplitTc * 4 + 4) * 4;
+    m.wred = o;  // float [2][8 heads][4 warps] block maxima + [8][4] row sums
+    o += (2 * 8 * 4 + 8 * 4) * 4;
+    m.stat = o;  // float m[8], l[8]; uint32 tag
+    o += 2 * 8 * 4 + 16;
+    m.total = o;
+    return m;
+}
+__device__ __forceinline__ void sts_b16(uint32_t addr, uint16_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
+template <int G, bool FLAGGED>
+__device__ __forceinline__ void compressed_split_tc(const DecodeArgs& a, uint8_t* smem, uint32_t tmem, int unit, int split,
+                                                    int n_split, int blk0, int blk1, bool again) {
+    const mfb200_decode_params& p = a.p;
+    const int D = a.depth, NVD = a.nvd;
+    const TcSmemMap sm = tc_smem_map(a.slot_nz_bytes, D, NVD);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t lane = lane_id();
+    const int nb = blk1 - blk0;
+    const int b = unit / p.kv_heads;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);
+    float* stat = reinterpret_cast<float*>(smem + sm.stat);
+    float* wred = reinterpret_cast<float*>(smem + sm.wred);
+    uint32_t* segk = reinterpret_cast<uint32_t*>(smem + sm.segk);
+    uint32_t* segv = reinterpret_cast<uint32_t*>(smem + sm.segv);
+    const uint32_t slot_bytes = 1024u + a.slot_nz_bytes;
+    const uint32_t kd_addr = smem_u32(smem + sm.kd), vd_addr = smem_u32(smem + sm.vd);
+    const uint32_t qb_addr = smem_u32(smem + sm.qb), pb_addr = smem_u32(smem + sm.pb);
+
+    // ---- prologue (see compressed_split) ----------------------------------------------------------------
+    const bool early_kv = (p.flags & MFB200_F_PDL_EARLY_KV) != 0;
+    pdl_launch_dependents();
+    if (!early_kv) pdl_wait_prior_grids();
+    if (again) __syncthreads();
+    {
+        const uint32_t* ki = p.k_idx + static_cast<int64_t>(unit) * p.idx_stride + static_cast<int64_t>(blk0) * 128;
+        const uint32_t* vi = p.v_idx + static_cast<int64_t>(unit) * p.idx_stride + static_cast<int64_t>(blk0) * 128;
+        for (int i = tid; i <= nb * 4; i += blockDim.x) {
+            segk[i] = __ldg(ki + i * 32);
+            segv[i] = __ldg(vi + i * 32);
+        }
+        for (int i = tid; i < 2 * kPbBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + sm.pb)[i] = 0u;  // rows >= G stay 0
+        if (tid == 0) {
+            if (again) {
+#pragma unroll
+                for (int i = 0; i < TcBars::kCount; ++i) mbar_inval(&bars[i]);
+            }
+            for (int i = 0; i < TcBars::kCount; ++i) mbar_init(&bars[i], 1);  // every mbarrier has exactly one arrival per phase
+            fence_mbar_init();
+        }
+    }
+    __syncthreads();
+    if (tid == 0) MFB_TRACE_AT(1);
+    const uint8_t* k_nz = static_cast<const uint8_t*>(p.k_nz) + p.k_nz_off[unit] * 16;
+    const uint8_t* v_nz = static_cast<const uint8_t*>(p.v_nz) + p.v_nz_off[unit] * 16;
+    const uint64_t* k_bmp = p.k_bmp + static_cast<int64_t>(unit) * p.bmp_stride + static_cast<int64_t>(blk0) * 128;
+    const uint64_t* v_bmp = p.v_bmp + static_cast<int64_t>(unit) * p.bmp_stride + static_cast<int64_t>(blk0) * 128;
+    int pn = 0, ps_slot = 0;
+    auto produce_until = [&](int limit) {
+        for (; pn < limit; ++pn, ++ps_slot) {
+            if (ps_slot == D) ps_slot = 0;
+#pragma unroll
+            for (int is_v = 0; is_v < 2; ++is_v) {
+                if (pn >= D) bar_sync((is_v ? NamedBars::kEmptyV : NamedBars::kEmptyK) + ps_slot, kHandoffThreads);
+                if (lane == 0) {
+                    uint64_t* full = &bars[(is_v ? TcBars::kFullV : TcBars::kFullK) + ps_slot];
+                    const uint32_t* seg = is_v ? segv : segk;
+                    const uint32_t off0 = seg[pn * 4], bytes = (seg[pn * 4 + 4] - off0) * 4u;
+                    const bool fits = bytes <= static_cast<uint32_t>(a.slot_nz_bytes);
+                    uint8_t* dst = smem + (is_v ? sm.slots_v : sm.slots_k) + ps_slot * slot_bytes;
+                    mbar_expect_tx(full, 1024u + ((fits && bytes) ? bytes : 0u));
+                    bulk_g2s(dst, (is_v ? v_bmp : k_bmp) + pn * 128, 1024u, full);
+                    if (fits && bytes) bulk_g2s(dst + 1024, (is_v ? v_nz : k_nz) + static_cast<uint64_t>(off0) * 4u, bytes, full);
+                }
+                __syncwarp();
+            }
+        }
+    };
+    if (warp == kWarpProducerTc) produce_until(nb < D ? nb : D);
+    if (early_kv) pdl_wait_prior_grids();
+    if (tid == 0) {
+        MFB_TRACE_AT(2);
+        reinterpret_cast<uint32_t*>(stat)[16] = ld_relaxed_u32(epoch_ptr(p, unit)) + 1u;  // this launch's partial tag
+    }
+    {   // q as the K-major B operand of the score MMAs: [channel group][row g][8 channels]; rows >= G are zero
+        const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
+        __half* qb = reinterpret_cast<__half*>(smem + sm.qb);
+        for (int i = tid; i < kQbBytes / 2; i += blockDim.x) {
+            const int kg = i >> 6, row = (i >> 3) & 7, e = i & 7;
+            qb[i] = row < G ? q[row * kHeadDim + kg * 8 + e] : __ushort_as_half(0);
+        }
+    }
+    fence_async_smem();  // qb / the zeroed p buffers were written through the generic proxy, the MMAs read them through the async one
+    __syncthreads();
+    if (tid == 0) {
+        MFB_TRACE_AT(3);
+        MFB_TRACE_VAL(12, static_cast<unsigned long long>(nb));
+    }
+    float* ored = reinterpret_cast<float*>(smem + sm.slots_k);  // [G][128], written when the rings are idle
+
+    if (warp == kWarpProducerTc) {
+        // =========================== producer ===========================
+        produce_until(nb);
+        for (int j = nb > D ? nb - D : 0; j < nb; ++j) {  // drain the last ring-full's arrivals (see compressed_split)
+            bar_sync(NamedBars::kEmptyK + j % D, kHandoffThreads);
+            bar_sync(NamedBars::kEmptyV + j % D, kHandoffThreads);
+        }
+    } else if (warp == kWarpMmaS) {
+        // =========================== score MMAs: S[n&1] = Kd[n&1] . q^T ===========================
+        for (int n = 0; n < nb; ++n) {
+            const int buf = n & 1;
+            const uint32_t u = n >> 1;
+            bar_sync(TcNamed::kKdFull + buf, kHandoffThreads);  // the 4 K decode warps have stored block n
+            if (lane == 0) {
+                if (u >= 1) mbar_wait(&bars[TcBars::kSEmpty + buf], (u - 1) & 1);
+                tc_fence_after();
+                const uint32_t a_lo = umma_desc_lo(kd_addr + buf * kDenseBytes, kLboK), b_lo = umma_desc_lo(qb_addr, 128);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_f16(tmem + 8 * buf, a_lo + ks * (2 * kLboK >> 4), umma_desc_hi(kTcSbo), b_lo + ks * (256 >> 4), umma_desc_hi(128),
+                             kIdescS, ks > 0);
+                umma_commit(&bars[TcBars::kKdEmpty + buf]);
+                umma_commit(&bars[TcBars::kSFull + buf]);
+            }
+            __syncwarp();
+        }
+        // every commit of this thread has landed before the split ends (a flat-plan CTA re-initialises the barriers); only
+        // the LAST completion of a barrier can be waited for (a parity wait on an older phase of a barrier that has
+        // advanced twice since blocks forever)
+        if (lane == 0) {
+            for (int j = nb > 2 ? nb - 2 : 0; j < nb; ++j) {
+                mbar_wait(&bars[TcBars::kKdEmpty + (j & 1)], (j >> 1) & 1);
+                mbar_wait(&bars[TcBars::kSFull + (j & 1)], (j >> 1) & 1);
+            }
+        }
+    } else if (warp == kWarpMmaO) {
+        // =========================== output MMAs: O[n&1] = Vd . p[n&1]^T ===========================
+        for (int n = 0; n < nb; ++n) {
+            const int buf = n & 1;
+            const uint32_t u = n >> 1;
+            const int vb = NVD == 2 ? buf : 0;
+            bar_sync(TcNamed::kVdFull + vb, kHandoffThreads);  // the 4 V decode warps have stored block n
+            bar_sync(TcNamed::kPFull + buf, kHandoffThreads);  // the 4 epilogue warps have stored p of block n
+            if (lane == 0) {
+                if (u >= 1) mbar_wait(&bars[TcBars::kOEmpty + buf], (u - 1) & 1);
+                tc_fence_after();
+                const uint32_t a_lo = umma_desc_lo(vd_addr + vb * kDenseBytes, kLboV), b_lo = umma_desc_lo(pb_addr + buf * kPbBytes, 128);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_f16(tmem + 16 + 16 * buf, a_lo + ks * (2 * kLboV >> 4), umma_desc_hi(kTcSbo), b_lo + ks * (256 >> 4), umma_desc_hi(0),
+                             kIdescO, ks > 0);
+                umma_commit(&bars[TcBars::kVdEmpty + vb]);
+                umma_commit(&bars[TcBars::kPEmpty + buf]);
+                umma_commit(&bars[TcBars::kOFull + buf]);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            for (int j = nb > 2 ? nb - 2 : 0; j < nb; ++j) {
+                if (NVD == 2 || j == nb - 1) {
+                    const int vb = NVD == 2 ? (j & 1) : 0;
+                    const uint32_t uv = NVD == 2 ? (j >> 1) : static_cast<uint32_t>(j);
+                    mbar_wait(&bars[TcBars::kVdEmpty + vb], uv & 1);
+                }
+                mbar_wait(&bars[TcBars::kPEmpty + (j & 1)], (j >> 1) & 1);
+                mbar_wait(&bars[TcBars::kOFull + (j & 1)], (j >> 1) & 1);
+            }
+        }
+    } else if (warp >= kWarpEpi0) {
+        // =========================== epilogue: online softmax + output accumulation ===========================
+        // S rows (tokens) 16e..16e+15 of an M = 64 accumulator live in lanes 0..15 of TMEM lane quadrant e = this warp;
+        // O rows (channels) 32e..32e+31 of the M = 128 accumulator in all 32 lanes of the same quadrant.
+        // Iteration n: [S(n) and O(n-2) are complete] -> load both -> fold O(n-2) -> softmax(n) -> publish p(n).
+        const int ew = warp - kWarpEpi0;
+        const bool valid = lane < 16;
+        const int t = 16 * ew + static_cast<int>(lane & 15);
+        const uint32_t tlane = tmem + (static_cast<uint32_t>(32 * ew) << 16);
+        const bool ref_round = (p.flags & MFB200_F_REF_SCORE_ROUNDING) != 0;
+        const float rdiv = 1.0f / p.score_div;
+        const __half* mask = p.mask ? static_cast<const __half*>(p.mask) + static_cast<int64_t>(b) * p.mask_stride : nullptr;
+        float m_run[G], l_part[G], o_acc[G], corr1[G], corr2[G];  // corr1 / corr2: rescale factors of blocks n-1 / n-2
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            m_run[g] = -INFINITY;
+            l_part[g] = o_acc[g] = 0.f;
+            corr1[g] = corr2[g] = 0.f;
+        }
+        auto fold = [&](int j, const float (&cr)[G]) {  // o = o * corr_j + O_j ; the caller has made sure O_j is complete
+            float o[8];
+            tmem_ld8(tlane + 16 + 16 * (j & 1), o);
+#pragma unroll
+            for (int g = 0; g < G; ++g) o_acc[g] = fmaf(o_acc[g], cr[g], o[g]);
+        };
+        for (int n = 0; n < nb; ++n) {
+            const int buf = n & 1;
+            const uint32_t u = n >> 1;
+            const float mk = (mask && valid) ? __half2float(mask[(blk0 + n) * kBlockTokens + t]) : 0.f;
+            if (ew == 0) {
+                mbar_wait(&bars[TcBars::kSFull + buf], u & 1);
+                if (u >= 1) {
+                    mbar_wait(&bars[TcBars::kOFull + buf], (u - 1) & 1);   // MMA-O(n-2) done: O[buf] complete ...
+                    mbar_wait(&bars[TcBars::kPEmpty + buf], (u - 1) & 1);  // ... and p[buf] free again
+                }
+            }
+            bar_sync(TcNamed::kEpi, 128);
+            tc_fence_after();
+            float s[8];
+            tmem_ld8(tlane + 8 * buf, s);
+            if (u >= 1) fold(n - 2, corr2);
+            tc_fence_before();
+            float x[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float v = ref_round_score_fast(s[g], p.score_div, rdiv, ref_round);
+                if (mask) v = fmaxf(v + mk, -65504.f);
+                x[g] = valid ? v * kLog2e : -INFINITY;  // log2 domain from here on (m, the stored partial maxima are converted back)
+                float mx = x[g];
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                if (lane == 0) wred[(buf * 8 + g) * 4 + ew] = mx;
+            }
+            bar_sync(TcNamed::kEpi, 128);  // the four warps' block maxima are in wred; every warp has read S[buf] and O[buf]
+            if (ew == 0 && lane == 0) {
+                mbar_arrive_cta(&bars[TcBars::kSEmpty + buf]);
+                if (u >= 1) mbar_arrive_cta(&bars[TcBars::kOEmpty + buf]);
+            }
+            uint16_t ph[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wred + (buf * 8 + g) * 4);
+                const float m_new = fmaxf(m_run[g], fmaxf(fmaxf(w4.x, w4.y), fmaxf(w4.z, w4.w)));
+                corr2[g] = corr1[g];
+                corr1[g] = ex2_fast(m_run[g] - m_new);  // ex2(-inf) = 0 on the first block
+                const float pv = ex2_fast(x[g] - m_new);  // invalid lanes: ex2(-inf) = 0
+                l_part[g] = fmaf(l_part[g], corr1[g], pv);
+                m_run[g] = m_new;
+                ph[g] = __half_as_ushort(__float2half_rn(pv));
+            }
+            if (valid) {
+                const uint32_t pa = pb_addr + buf * kPbBytes + (t >> 3) * 128 + (t & 7) * 2;
+#pragma unroll
+                for (int g = 0; g < G; ++g) sts_b16(pa + g * 16, ph[g]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            bar_arrive(TcNamed::kPFull + buf, kHandoffThreads);
+        }
+        // the last two blocks' outputs: block nb-2 (rescaled by corr of nb-2 ... see below) then nb-1
+        for (int j = nb > 2 ? nb - 2 : 0; j < nb; ++j) {
+            if (ew == 0) mbar_wait(&bars[TcBars::kOFull + (j & 1)], (j >> 1) & 1);
+            bar_sync(TcNamed::kEpi, 128);
+            tc_fence_after();
+            if (j == nb - 1) fold(j, corr1);
+            else fold(j, corr2);
+            tc_fence_before();
+        }
+        // split results: o [G][128], m, l
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            ored[g * 128 + 32 * ew + lane] = o_acc[g];
+            float v = l_part[g];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) wred[64 + g * 4 + ew] = v;
+        }
+        bar_sync(TcNamed::kEpi, 128);
+        if (ew == 0 && lane == 0) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                stat[g] = m_run[g] * (1.0f / kLog2e);  // back from the log2 domain: partial maxima are merged in natural units
+                stat[8 + g] = wred[64 + g * 4] + wred[64 + g * 4 + 1] + wred[64 + g * 4 + 2] + wred[64 + g * 4 + 3];
+            }
+        }
+    } else {
+        // =========================== K / V decode warps ===========================
+        // (one instantiation per stream: the stream-dependent constants fold away instead of being re-selected per block)
+        auto decode_role = [&](auto is_v_tag) {
+            constexpr bool is_v = decltype(is_v_tag)::value;
+            const int w = warp & 3;
+            const LaneConst lc = make_lane_const();
+            uint2* rec = reinterpret_cast<uint2*>(smem + sm.rec) + warp * 64;
+            const uint2* my_rec = rec + lc.half;
+            const uint32_t* seg = is_v ? segv : segk;
+            const uint8_t* nz_g = is_v ? v_nz : k_nz;
+            const uint32_t slots_off = is_v ? sm.slots_v : sm.slots_k;
+            constexpr int full0 = is_v ? TcBars::kFullV : TcBars::kFullK, empty0 = is_v ? NamedBars::kEmptyV : NamedBars::kEmptyK;
+            constexpr int dfull0 = is_v ? TcNamed::kVdFull : TcNamed::kKdFull, dempty0 = is_v ? TcBars::kVdEmpty : TcBars::kKdEmpty;
+            constexpr uint32_t lbo = is_v ? kLboV : kLboK;
+            // destination of tile 0 of this warp for this lane: MN offset of the lane's position pair + the warp's K groups
+            //   K: tile = channel 32w + j, positions = tokens     -> K group 4w + (j >> 3), MN = tokens
+            //   V: tile = token 32(w&1) + j of channel half w>>1  -> K group 4(w&1) + (j >> 3), MN = channels 64(w>>1) + ...
+            const uint32_t lane_off = (lane >> 2) * kTcSbo + (lane & 3) * 4;
+            const uint32_t dst0 = is_v ? vd_addr + 8 * (w >> 1) * kTcSbo + 4 * (w & 1) * kLboV + lane_off
+                                       : kd_addr + 4 * w * kLboK + lane_off;
+            const bool single = is_v && NVD == 1;  // one dense buffer, used by every block
+            int s = 0;
+            uint32_t par = 0;
+            for (int n = 0; n < nb; ++n, ++s) {
+                if (s == D) {
+                    s = 0;
+                    par ^= 1;
+                }
+                const uint8_t* sl = smem + slots_off + s * slot_bytes;
+                const uint32_t sg0 = seg[n * 4];
+                const bool fits = (seg[n * 4 + 4] - sg0) * 4u <= static_cast<uint32_t>(a.slot_nz_bytes);
+                const uint8_t* gblk = nz_g + static_cast<uint64_t>(sg0) * 4u;
+                const uint32_t nz_addr = (fits ? smem_u32(sl + 1024) : 0u) + (seg[n * 4 + w] - sg0) * 4u;
+                mbar_wait(&bars[full0 + s], par);
+                build_records(reinterpret_cast<const uint64_t*>(sl) + w * 32, nz_addr, rec);
+                __syncwarp();
+                const int db = single ? 0 : (n & 1);
+                const uint32_t ud = single ? static_cast<uint32_t>(n) : static_cast<uint32_t>(n >> 1);
+                if (ud >= 1) mbar_wait(&bars[dempty0 + db], (ud - 1) & 1);  // the MMAs that read this dense buffer last are done
+                if (fits) decode_to_umma32<true>(my_rec, lc, gblk, dst0 + db * kDenseBytes, lbo);
+                else decode_to_umma32<false>(my_rec, lc, gblk, dst0 + db * kDenseBytes, lbo);
+                fence_async_smem();  // this lane's dense stores -> visible to the tensor core's (async proxy) reads
+                __syncwarp();
+                bar_arrive(empty0 + s, kHandoffThreads);   // ring slot free
+                bar_arrive(dfull0 + db, kHandoffThreads);  // dense block ready
+                if (!is_v && tid == 0 && n == 0) MFB_TRACE_AT(4);
+                if (!is_v && tid == 0 && n == nb - 1) MFB_TRACE_AT(5);
+                if (is_v && tid == kWarpV0 * 32 && n == 0) MFB_TRACE_AT(6);
+                if (is_v && tid == kWarpV0 * 32 && n == nb - 1) MFB_TRACE_AT(7);
+            }
+        };
+        if (warp >= kWarpV0) decode_role(std::true_type{});
+        else decode_role(std::false_type{});
+    }
+    __syncthreads();
+    if (tid == 0) MFB_TRACE_AT(8);
+    publish_or_merge<G, FLAGGED>(a, unit, split, n_split, reinterpret_cast<const uint32_t*>(stat)[16], ored, stat, stat + 8,
+                                 reinterpret_cast<float*>(smem + sm.slots_v));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -814,7 +1247,7 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
     }
     {
         const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
-        for (int i = tid; i < G * kHeadDim; i += kAttnThreads) qs[win_q_index(i >> 7, i & 127)] = __half2float(q[i]);
+        for (int i = tid; i < G * kHeadDim; i += blockDim.x) qs[win_q_index(i >> 7, i & 127)] = __half2float(q[i]);
     }
     __syncthreads();  // q staged, barrier initialised
     mbar_wait(bar, 0);
@@ -927,7 +1360,7 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
         for (int g = 0; g < G; ++g) *reinterpret_cast<float4*>(red + (warp * G + g) * 128 + 4 * lane) = make_float4(o[g][0], o[g][1], o[g][2], o[g][3]);
     }
     __syncthreads();
-    for (int i = tid; i < G * 128; i += kAttnThreads) {
+    for (int i = tid; i < G * 128; i += blockDim.x) {
         const int g = i >> 7, c = i & 127;
         float s = 0.f;
 #pragma unroll
@@ -943,7 +1376,7 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
 // flagged merge.  (The uniform kernels carry no segment-loop state in registers; the ticket kernels carry none of
 // the flagged protocol's code: sharing instantiations cost 2-3 % through register pressure.)
 template <int G, int MODE>
-__global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 ? 2 : 1))) sparse_decode_attn_kernel(const __grid_constant__ DecodeArgs a) {
+__global__ void __launch_bounds__(cta_threads(G), (G <= 1 ? MFB_G1_CTAS : (G <= 4 ? 2 : 1))) sparse_decode_attn_kernel(const __grid_constant__ DecodeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     // 1-D grid, long CTAs first: all compressed splits of all units, then the short window splits.
 #ifdef MFB_POISON
@@ -971,10 +1404,23 @@ __global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 
     constexpr bool FLAT = MODE == 1, FLAGGED = MODE == 2;
     const int n_comp = FLAT ? a.flat_ctas : n_base + a.n_extra;
     if (id < n_comp) {
+        uint32_t tmem = 0;
+        if constexpr (use_tc(G)) {  // tensor-memory accumulators S[2], O[2]: allocated once per CTA by the producer warp
+            __shared__ uint32_t s_tmem;
+            if ((threadIdx.x >> 5) == kWarpProducerTc) tmem_alloc(&s_tmem);
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            tmem = s_tmem;
+        }
+        auto run_split = [&](int unit, int split, int n_split, int b0, int b1, bool again) {
+            if constexpr (use_tc(G)) compressed_split_tc<G, FLAGGED>(a, smem, tmem, unit, split, n_split, b0, b1, again);
+            else compressed_split<G, FLAGGED>(a, smem, unit, split, n_split, b0, b1, again);
+        };
         if constexpr (!FLAT) {  // uniform mode: split `id / units` of unit `id % units`
             const int unit = id < n_base ? id % units : id - n_base, split = id < n_base ? id / units : a.n_csplit;
             const int nc = unit_csplits(a, unit);
-            compressed_split<G, FLAGGED>(a, smem, unit, split, nc + a.n_wsplit, split * nblk / nc, (split + 1) * nblk / nc, false);
+            run_split(unit, split, nc + a.n_wsplit, split * nblk / nc, (split + 1) * nblk / nc, false);
         } else {
             // flat mode: an even cut of all units*nblk blocks, processed as segments cut at unit boundaries (one partial
             // per segment).  The segment arithmetic is redone per segment from opaque copies of (id, j) so that nothing
@@ -988,10 +1434,14 @@ __global__ void __launch_bounds__(kAttnThreads, (G <= 1 ? MFB_G1_CTAS : (G <= 4 
                 const int b0 = jv == 0 ? cur - u0 : 0;
                 const int b1 = min(static_cast<uint32_t>(nblk), end - u0);
                 const bool more = u0 + nblk < end;
-                compressed_split<G, FLAGGED>(a, smem, unit, idv - static_cast<int>(flat_owner(a, u0)), unit_csplits(a, unit) + a.n_wsplit,
-                                    b0, b1, j > 0);
+                run_split(unit, idv - static_cast<int>(flat_owner(a, u0)), unit_csplits(a, unit) + a.n_wsplit, b0, b1, j > 0);
                 if (!more) break;
             }
+        }
+        if constexpr (use_tc(G)) {
+            tc_fence_before();
+            __syncthreads();
+            if ((threadIdx.x >> 5) == kWarpProducerTc) tmem_dealloc(tmem);
         }
     } else {  // dense-window chunks come after all compressed CTAs
         const int unit = (id - n_comp) % units, wchunk = (id - n_comp) / units;
@@ -1014,8 +1464,8 @@ static int pick_depth(int slot_nz_bytes) { return slot_nz_bytes <= 8 * 1024 ? 3 
 
 template <int G, int MODE>
 static int launch_decode(const DecodeArgs& a, cudaStream_t s) {
-    const SmemMap sm = smem_map(G, a.slot_nz_bytes, a.depth);
-    size_t smem = (a.n_csplit > 0 || a.n_extra > 0 || a.flat_ctas > 0) ? sm.total : 0;
+    const size_t comp_smem = use_tc(G) ? tc_smem_map(a.slot_nz_bytes, a.depth, a.nvd).total : smem_map(G, a.slot_nz_bytes, a.depth).total;
+    size_t smem = (a.n_csplit > 0 || a.n_extra > 0 || a.flat_ctas > 0) ? comp_smem : 0;
     if (a.n_wsplit > 0) smem = smem > window_smem_bytes(G) ? smem : window_smem_bytes(G);
     static size_t configured[kMaxDevices] = {0};  // per device, per instantiation
     if (smem > 0) {
@@ -1025,7 +1475,7 @@ static int launch_decode(const DecodeArgs& a, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
     const int units = a.p.batch * a.p.kv_heads;
     cfg.gridDim = dim3((a.flat_ctas > 0 ? a.flat_ctas : a.n_csplit * units + a.n_extra) + a.n_wsplit * units);
-    cfg.blockDim = dim3(kAttnThreads);
+    cfg.blockDim = dim3(cta_threads(G));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -1052,6 +1502,7 @@ struct Plan {
 //    resident CTA slots, CTAs may cross unit boundaries -> no wave-quantisation loss for mid-size batches.
 // plan_hint (mfb200_decode_params::plan_hint): 0 = automatic, n > 0 = flat plan with n compressed CTAs, < 0 = never flat.
 static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win_len, int sm_count, int plan_hint = 0) {
+    const int kMaxBlocksPerSplit = use_tc(groups) ? kMaxBlocksPerSplitTc : mfb::kMaxBlocksPerSplit;  // shadows the constant
     Plan pl = {0, 0, (win_len + kWinTokensPerSplit - 1) / kWinTokensPerSplit, 0, 0, 0, 0, 0};
     const int64_t units = static_cast<int64_t>(batch) * kv_heads;
     const int nblk = comp_len / kBlockTokens;
@@ -1167,7 +1618,7 @@ extern "C" int mfb200_decode_plan_check(int batch, int kv_heads, int groups, int
     auto segment = [&](int id, int unit, int split, int b0, int b1) {
         const int nc = unit_csplits(a, unit);
         if (unit < 0 || unit >= units || split < 0 || split >= nc || nc + pl.n_wsplit > pl.max_split || b0 != next_blk[unit] || b1 <= b0 ||
-            b1 > nblk || b1 - b0 > kMaxBlocksPerSplit || used[static_cast<size_t>(unit) * pl.max_split + split]) {
+            b1 > nblk || b1 - b0 > (use_tc(groups) ? kMaxBlocksPerSplitTc : kMaxBlocksPerSplit) || used[static_cast<size_t>(unit) * pl.max_split + split]) {
             if (!err) set_error("plan_check: CTA %d segment (unit %d, slot %d of %d, blocks [%d, %d)) is inconsistent (next block %d, max_split %d)",
                                 id, unit, split, nc, b0, b1, unit >= 0 && unit < units ? next_blk[unit] : -1, pl.max_split);
             err = 1;
@@ -1287,6 +1738,18 @@ extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb
     }
     a.slot_nz_bytes = pick_slot_nz_bytes(p);
     a.depth = pick_depth(a.slot_nz_bytes);
+    a.nvd = 1;
+    if (use_tc(p->groups)) {
+        // two CTAs per SM: 227 KB / 2 minus the per-CTA reservation.  Ring depth 2 (the dense operand buffers are the
+        // second pipeline stage); a second dense V buffer if it still fits.
+        constexpr uint32_t kBudget = (233472 / 2) - 1024;  // 228 KB per SM, 1 KB reserved per CTA
+        a.depth = 2;
+        if (tc_smem_map(a.slot_nz_bytes, 2, 2).total <= kBudget) a.nvd = 2;
+        else if (tc_smem_map(a.slot_nz_bytes - 512, 2, 2).total <= kBudget) {  // half a KB less staging per slot buys the buffer
+            a.slot_nz_bytes -= 512;
+            a.nvd = 2;
+        }
+    }
     auto s = static_cast<cudaStream_t>(stream);
     switch (p->groups) {
         case 1: return a.flat_ctas > 0 ? launch_decode<1, 1>(a, s) : (a.flagged ? launch_decode<1, 2>(a, s) : launch_decode<1, 0>(a, s));

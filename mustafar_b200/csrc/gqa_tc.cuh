@@ -32,15 +32,16 @@ constexpr uint32_t kTmemCols = 64;          // S[2] at columns 0 / 8, O[2] at co
 constexpr uint32_t kIdescS = (1u << 4) | (1u << 15) | (1u << 17) | (4u << 24);   // f32 acc, f16 x f16, A MN-major, N=8,  M=64
 constexpr uint32_t kIdescO = (1u << 4) | (1u << 15) | (2u << 17) | (8u << 24);   //                                  N=16, M=128
 
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-    return static_cast<uint64_t>((addr >> 4) & 0x3fffu) | (static_cast<uint64_t>((lbo >> 4) & 0x3fffu) << 16) |
-           (static_cast<uint64_t>((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);  // version 1, no swizzle
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// Shared-memory operand descriptor (64 bit): [0,14) address >> 4, [16,30) LBO >> 4, [32,46) SBO >> 4, [46,48) version = 1,
+// layout type (bits 61-63) 0 = no swizzle.  Split into its two words: only the low one changes from MMA to MMA.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3fffu) | (((lbo >> 4) & 0x3fffu) << 16); }
+__device__ __forceinline__ constexpr uint32_t umma_desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3fffu) | (1u << 14); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                         uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar` when all MMAs issued so far by this thread are done
@@ -74,20 +75,22 @@ __device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v) {
 }
 
 // Decompress the warp's 32 tiles (records at `rec`) into a UMMA operand tile: tile j lands at `dst + (j & 7) * 16 +
-// (j >> 3) * LBO` (8 K rows of one core-matrix row group, then the next K group), `dst` already carries the lane's MN
-// offset ((lane >> 2) * 144 + (lane & 3) * 4) and the warp's first K group.
+// (j >> 3) * lbo` (8 K rows of one core-matrix row group, then the next K group), `dst` already carries the lane's MN
+// offset ((lane >> 2) * 144 + (lane & 3) * 4) and the warp's first K group.  One instantiation serves K and V tiles
+// (lbo is a run-time value) and only 8 tiles are unrolled: the kernel's warp roles all run different code, so its
+// instruction footprint matters (the fully unrolled first version stalled on instruction fetch).
 // Per tile: LDS.64 record, LOP3, POPC, IMAD, 2 x LDS.U16, 2 x LOP3->P, 2 x SEL, PRMT, STS.32.  The rank is taken
 // INCLUSIVE of the lane's first position (one popc over `above | bit0`): the second value then sits at that rank and
 // the first one slot before it, so neither load depends on a bit test.
-template <int LBO, bool NZ_SHARED>
-__device__ __forceinline__ void decode_to_umma32(const uint2* rec, const LaneConst& lc, const uint8_t* gbase, uint32_t dst) {
+template <bool NZ_SHARED>
+__device__ __forceinline__ void decode_to_umma32(const uint2* rec, const LaneConst& lc, const uint8_t* gbase, uint32_t dst, uint32_t lbo) {
     const uint32_t above1 = lc.above | lc.bit0;
-#pragma unroll
-    for (int j0 = 0; j0 < 32; j0 += 8) {
+#pragma unroll 1
+    for (int j0 = 0; j0 < 32; j0 += 8, rec += 16, dst += lbo) {
         uint32_t packed[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const uint2 r = rec[2 * (j0 + i)];
+            const uint2 r = rec[2 * i];
             uint32_t addr1;  // address of the value of the lane's SECOND position (if set); the first one's is addr1 - 2
             asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr1) : "r"(__popc(r.x & above1)), "r"(r.y));
             const bool b0 = (r.x & lc.bit0) != 0, b1 = (r.x & lc.bit1) != 0;
@@ -103,7 +106,7 @@ __device__ __forceinline__ void decode_to_umma32(const uint2* rec, const LaneCon
             packed[i] = __byte_perm(b0 ? a : 0u, b1 ? b : 0u, 0x5410);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sts_b32(dst + (j0 + i) * 16 + (j0 >> 3) * LBO, packed[i]);
+        for (int i = 0; i < 8; ++i) sts_b32(dst + i * 16, packed[i]);
     }
 }
 
