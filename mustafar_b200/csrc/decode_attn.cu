@@ -34,7 +34,7 @@
 #include "sparse_tile.cuh"
 
 #ifndef MFB_GQA_TC
-#define MFB_GQA_TC 1  // 1: G >= 4 contracts on tcgen05 (gqa_tc.cuh); 0: the round-1 mma.sync path (gqa_mma.cuh), kept for A/B runs
+#define MFB_GQA_TC 0  // 0: G >= 4 contracts register fragments with mma.sync (gqa_mma.cuh); 1: the tcgen05 / TMEM variant (gqa_tc.cuh), kept for A/B runs
 #endif
 
 namespace mfb {
@@ -119,8 +119,8 @@ __host__ __device__ inline SmemMap smem_map(int G, int slot_nz_bytes, int depth)
     o += ((Bars::kCount * 8 + 15) / 16) * 16;
     m.rec = o;  // uint2 [8 consumer warps][32 tiles][2]
     o += 2 * kTileWarps * 64 * 8;
-    m.qs = o;  // half [128][G]
-    o += kHeadDim * G * 2;
+    m.qs = o;  // half [128][G]  (G >= 4: [G][kQPitch], channels contiguous)
+    o += (G >= 4 ? G * kQPitch : kHeadDim * G) * 2;
     m.spart = o;  // float [2][4 warps][G][sp_pitch]; reused for the final cross-warp reduction of o
     o += 2 * kTileWarps * G * (G >= 4 ? kTcRowPitch : 64) * 4;
     m.ps = o;  // half [2][64][G]  (G >= 4: [2][G][kTcRowPitch], token pairs contiguous)
@@ -133,8 +133,8 @@ __host__ __device__ inline SmemMap smem_map(int G, int slot_nz_bytes, int depth)
     o += (kMaxBlocksPerSplit * 4 + 4) * 4;
     m.segv = o;
     o += (kMaxBlocksPerSplit * 4 + 4) * 4;
-    m.dense = o;  // G >= 4 (tensor-core variant): one 32 x 64 fp16 buffer per tile warp
-    if (G >= 4) o += 2 * kTileWarps * kDenseWarpBytes;
+    m.dense = o;  // G >= 4: 64 bytes of zeros, the B fragment of the lanes that are not live in an MMA (gqa_mma.cuh)
+    if (G >= 4) o += 64;
     m.total = o;
     return m;
 }
@@ -146,7 +146,7 @@ __device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepco
 
 // Timeline instrumentation (`make trace`, tools/trace_attn.py): per-CTA phase timestamps from %globaltimer.
 #ifdef MFB_TRACE
-constexpr int kTraceSlots = 16, kTraceMaxCtas = 8192;
+constexpr int kTraceSlots = 32, kTraceMaxCtas = 8192;  // 0-15 timestamps / values, 16-31 per-role cycle accumulators
 __device__ unsigned long long g_trace[2 * kTraceMaxCtas * kTraceSlots];  // two launches: flag bit 0x100 picks the half
 __shared__ int s_trace_half;  // set by thread 0 at kernel entry (barriers follow before any other thread traces)
 __device__ __forceinline__ void trace_val(int k, unsigned long long v) {
@@ -160,9 +160,17 @@ __device__ __forceinline__ void trace_at(int k) {
 }
 #define MFB_TRACE_AT(k) trace_at(k)
 #define MFB_TRACE_VAL(k, v) trace_val(k, v)
+// cycle accounting of one warp role: MFB_TACC_INIT(n) declares n accumulators, MFB_TACC(i) adds the SM clocks since the
+// previous mark to accumulator i, MFB_TACC_STORE(slot0, n, cond) writes them to trace slots slot0.. (one lane)
+#define MFB_TACC_INIT(n) long long tacc_[n] = {}; long long tacc_t_ = clock64()
+#define MFB_TACC(i) do { const long long now_ = clock64(); tacc_[i] += now_ - tacc_t_; tacc_t_ = now_; } while (0)
+#define MFB_TACC_STORE(slot0, n, cond) do { if (cond) for (int i_ = 0; i_ < (n); ++i_) trace_val((slot0) + i_, static_cast<unsigned long long>(tacc_[i_])); } while (0)
 #else
 #define MFB_TRACE_AT(k) ((void)0)
 #define MFB_TRACE_VAL(k, v) ((void)0)
+#define MFB_TACC_INIT(n) ((void)0)
+#define MFB_TACC(i) ((void)0)
+#define MFB_TACC_STORE(slot0, n, cond) ((void)0)
 #endif
 
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
@@ -523,7 +531,12 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     }
     {
         const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
-        for (int i = tid; i < G * kHeadDim; i += blockDim.x) qs[(i & 127) * G + (i >> 7)] = q[i];
+        if constexpr (G >= 4) {
+            for (int i = tid; i < G * kHeadDim; i += blockDim.x) qs[(i >> 7) * kQPitch + (i & 127)] = q[i];
+            if (tid < 16) reinterpret_cast<uint32_t*>(smem + sm.dense)[tid] = 0u;
+        } else {
+            for (int i = tid; i < G * kHeadDim; i += blockDim.x) qs[(i & 127) * G + (i >> 7)] = q[i];
+        }
     }
     __syncthreads();  // q staged (threads of every warp contribute) before the K warps read it
     if (tid == 0) {
@@ -533,10 +546,9 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     float o_acc[G][2];
 #pragma unroll
     for (int g = 0; g < G; ++g) o_acc[g][0] = o_acc[g][1] = 0.f;
-    float tc_o[8][2];      // tensor-core variant: V warps' out[g = tc_o_gid][8*nt + 2*tig .. +1]
-    uint32_t tc_o_gid = 0;
+    [[maybe_unused]] float gq_o[G >= 4 ? G / 2 : 1][4];  // G >= 4: the V warps' accumulator fragments (see gqa_mma.cuh for the layout)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tc_o[i][0] = tc_o[i][1] = 0.f;
+    for (int m = 0; m < (G >= 4 ? G / 2 : 1); ++m) gq_o[m][0] = gq_o[m][1] = gq_o[m][2] = gq_o[m][3] = 0.f;
 
     if (warp == kWarpProducer) {
         // =========================== producer ===========================
@@ -628,22 +640,10 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         const uint8_t* nz_g = is_v ? v_nz : k_nz;
         const uint32_t slots_off = is_v ? sm.slots_v : sm.slots_k;
         const int full0 = is_v ? Bars::kFullV : Bars::kFullK, empty0 = is_v ? NamedBars::kEmptyV : NamedBars::kEmptyK;
-        // tensor-core variant state: q A-fragments (K warps, constant) and the o accumulator fragments (V warps)
-        uint32_t qfrag[2][2] = {{0u, 0u}, {0u, 0u}};
-        float oacc[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
-        if constexpr (G >= 4) {
-            const uint32_t gid = lane >> 2, tig = lane & 3;
-            if (!is_v && gid < G) {
-                const uint32_t* q32 = reinterpret_cast<const uint32_t*>(static_cast<const __half*>(p.q) +
-                                                                        (static_cast<int64_t>(unit) * G + gid) * kHeadDim + 32 * w);
-                qfrag[0][0] = q32[tig];
-                qfrag[0][1] = q32[4 + tig];
-                qfrag[1][0] = q32[8 + tig];
-                qfrag[1][1] = q32[12 + tig];
-            }
-        }
+        // G >= 4: per-lane constants of the block-diagonal HMMA scheme (gqa_mma.cuh)
+        [[maybe_unused]] GqaLane<(G >= 4 ? G : 4)> gl;
+        if constexpr (G >= 4) gl = make_gqa_lane<G>();
+        [[maybe_unused]] const uint32_t zeros_addr = smem_u32(smem + sm.dense);
         int s = 0;
         uint32_t par = 0;
         for (int n = 0; n < nb; ++n, ++s) {
@@ -662,49 +662,55 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             build_records(reinterpret_cast<const uint64_t*>(sl) + w * 32, nz_addr, rec);
             __syncwarp();
             if constexpr (G >= 4) {
-                // ---------- tensor-core variant: decompress to the warp's dense buffer, then 16 HMMA ----------
-                const uint32_t dense_addr = smem_u32(smem + sm.dense) + warp * kDenseWarpBytes;
-                const uint32_t gid = lane >> 2, tig = lane & 3;
-                __syncwarp();  // the previous block's ldmatrix reads of the buffer are done
-                if (fits) decode_to_dense32<true>(my_rec, lc, gblk, dense_addr);
-                else decode_to_dense32<false>(my_rec, lc, gblk, dense_addr);
-                __syncwarp();
-                bar_arrive(empty0 + s, kHandoffThreads);  // ring slot no longer needed
+                // ---------- G >= 4: register-fragment HMMA, all G heads from one decode (gqa_mma.cuh) ----------
+                constexpr int NM = G / 2;
                 if (!is_v) {
-                    // scores[g][token] += q[g][channels 32w..32w+31] . K : A = q rows (constant), B = dense (channel x token)
-                    float acc[8][4];
+                    // partial scores over channels 32w..32w+31: operand = q[g][channel]
+                    float acc[NM][4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-                    mma_dense32(dense_addr, qfrag, acc);
+                    for (int m = 0; m < NM; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+                    uint32_t oper[NM];
+#pragma unroll
+                    for (int m = 0; m < NM; ++m)
+                        oper[m] = gl.live_m == static_cast<uint32_t>(m) ? smem_u32(qs + gl.g_live * kQPitch + 32 * w) : zeros_addr;
+                    if (fits) tiles32_mma<G, true>(my_rec, lc, gblk, oper, acc);
+                    else tiles32_mma<G, false>(my_rec, lc, gblk, oper, acc);
+                    __syncwarp();
+                    bar_arrive(empty0 + s, kHandoffThreads);  // ring slot no longer needed
                     mbar_wait(&bars[Bars::kScEmpty + buf], par2 ^ 1);
-                    if (gid < G) {
-                        float* sp = spart + ((buf * kTileWarps + w) * G + gid) * kTcRowPitch + 2 * tig;
+                    float* sp = spart + ((buf * kTileWarps + w) * G + gl.g0) * kTcRowPitch;
 #pragma unroll
-                        for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<float2*>(sp + 8 * nt) = make_float2(acc[nt][0], acc[nt][1]);
+                    for (int m = 0; m < NM; ++m) {
+                        *reinterpret_cast<float2*>(sp + gl.pos[m]) = make_float2(acc[m][0], acc[m][2]);
+                        *reinterpret_cast<float2*>(sp + kTcRowPitch + gl.pos[m]) = make_float2(acc[m][1], acc[m][3]);
                     }
                     __syncwarp();
                     bar_arrive(NamedBars::kScFull + buf, kHandoffThreads);
+                    if (tid == 0 && n == 0) MFB_TRACE_AT(4);
+                    if (tid == 0 && n == nb - 1) MFB_TRACE_AT(5);
                 } else {
-                    // out[g][channel] += p[g][tokens] . V : A = p rows of this block, B = dense (token x channel)
+                    // out[g][channel] += p[g][token] * V over tokens 32(w&1)..+31: operand = p[g][token]
                     mbar_wait(&bars[Bars::kPFull + buf], par2);
-                    uint32_t pfrag[2][2] = {{0u, 0u}, {0u, 0u}};
-                    float c = 1.f;
-                    if (gid < G) {
-                        const uint32_t pa = smem_u32(ps + (buf * G + gid) * kTcRowPitch + 32 * (w & 1) + 2 * tig);
-                        pfrag[0][0] = lds_u32(pa);
-                        pfrag[0][1] = lds_u32(pa + 16);
-                        pfrag[1][0] = lds_u32(pa + 32);
-                        pfrag[1][1] = lds_u32(pa + 48);
-                        c = corr[buf * 8 + gid];
-                    }
-                    __syncwarp();
-                    bar_arrive(NamedBars::kPEmpty + buf, kHandoffThreads);
+                    const float c_lo = corr[buf * 8 + gl.g0], c_hi = corr[buf * 8 + gl.g0 + 1];
 #pragma unroll
-                    for (int nt = 0; nt < 8; ++nt) {
-                        oacc[nt][0] *= c;
-                        oacc[nt][1] *= c;
+                    for (int m = 0; m < NM; ++m) {
+                        gq_o[m][0] *= c_lo;
+                        gq_o[m][1] *= c_hi;
+                        gq_o[m][2] *= c_lo;
+                        gq_o[m][3] *= c_hi;
                     }
-                    mma_dense32(dense_addr, pfrag, oacc);
+                    uint32_t oper[NM];
+#pragma unroll
+                    for (int m = 0; m < NM; ++m)
+                        oper[m] = gl.live_m == static_cast<uint32_t>(m) ? smem_u32(ps + (buf * G + gl.g_live) * kTcRowPitch + 32 * (w & 1))
+                                                                        : zeros_addr;
+                    if (fits) tiles32_mma<G, true>(my_rec, lc, gblk, oper, gq_o);
+                    else tiles32_mma<G, false>(my_rec, lc, gblk, oper, gq_o);
+                    __syncwarp();
+                    bar_arrive(empty0 + s, kHandoffThreads);
+                    bar_arrive(NamedBars::kPEmpty + buf, kHandoffThreads);
+                    if (tid == kWarpV0 * 32 && n == 0) MFB_TRACE_AT(6);
+                    if (tid == kWarpV0 * 32 && n == nb - 1) MFB_TRACE_AT(7);
                 }
             } else if (!is_v) {
                 // K item: tiles = channels 32w .. 32w+31 -> partial scores of tokens (2*lane, 2*lane+1)
@@ -739,19 +745,6 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                 if (tid == kWarpV0 * 32 && n == nb - 1) MFB_TRACE_AT(7);
             }
         }
-        if constexpr (G >= 4) {
-            // hand the V warps' accumulator fragments over in the layout the final reduction expects
-            if (is_v) {
-                const uint32_t gid = lane >> 2, tig = lane & 3;
-                tc_o_gid = gid;
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt) {
-                    tc_o[nt][0] = oacc[nt][0];
-                    tc_o[nt][1] = oacc[nt][1];
-                }
-                (void)tig;
-            }
-        }
     }
     // ---- cross-warp reduction of o: V warps (0,1) hold channel half 0, (2,3) half 1 -------------------
     __syncthreads();
@@ -761,10 +754,12 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     if (warp >= kWarpV0 && warp < kWarpV0 + kTileWarps) {
         const int w = warp & 3;
         if constexpr (G >= 4) {
-            if (tc_o_gid < G) {
-                float* rp = red + (w * G + tc_o_gid) * 64 + 2 * (lane & 3);
+            const uint32_t gid = lane >> 2, tig = lane & 3;
 #pragma unroll
-                for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<float2*>(rp + 8 * nt) = make_float2(tc_o[nt][0], tc_o[nt][1]);
+            for (int m = 0; m < G / 2; ++m) {  // same D-fragment layout as the K side: heads g0, g0+1 of positions pos, pos+1
+                const uint32_t g0 = (2 * tig) % G, pos = 8 * gid + 2 * ((8 * m + 2 * tig) / G);
+                *reinterpret_cast<float2*>(red + (w * G + g0) * 64 + pos) = make_float2(gq_o[m][0], gq_o[m][2]);
+                *reinterpret_cast<float2*>(red + (w * G + g0 + 1) * 64 + pos) = make_float2(gq_o[m][1], gq_o[m][3]);
             }
         } else {
 #pragma unroll
@@ -950,12 +945,16 @@ __device__ __forceinline__ void compressed_split_tc(const DecodeArgs& a, uint8_t
         }
     } else if (warp == kWarpMmaS) {
         // =========================== score MMAs: S[n&1] = Kd[n&1] . q^T ===========================
+        MFB_TACC_INIT(3);  // 0 wait Kd, 1 wait S free, 2 issue
         for (int n = 0; n < nb; ++n) {
             const int buf = n & 1;
             const uint32_t u = n >> 1;
+            MFB_TACC(2);
             bar_sync(TcNamed::kKdFull + buf, kHandoffThreads);  // the 4 K decode warps have stored block n
+            MFB_TACC(0);
             if (lane == 0) {
                 if (u >= 1) mbar_wait(&bars[TcBars::kSEmpty + buf], (u - 1) & 1);
+                MFB_TACC(1);
                 tc_fence_after();
                 const uint32_t a_lo = umma_desc_lo(kd_addr + buf * kDenseBytes, kLboK), b_lo = umma_desc_lo(qb_addr, 128);
 #pragma unroll
@@ -967,6 +966,8 @@ __device__ __forceinline__ void compressed_split_tc(const DecodeArgs& a, uint8_t
             }
             __syncwarp();
         }
+        MFB_TACC(2);
+        MFB_TACC_STORE(27, 2, lane == 0);  // slots 27 (wait Kd), 28 (wait S free)
         // every commit of this thread has landed before the split ends (a flat-plan CTA re-initialises the barriers); only
         // the LAST completion of a barrier can be waited for (a parity wait on an older phase of a barrier that has
         // advanced twice since blocks forever)
@@ -978,14 +979,19 @@ __device__ __forceinline__ void compressed_split_tc(const DecodeArgs& a, uint8_t
         }
     } else if (warp == kWarpMmaO) {
         // =========================== output MMAs: O[n&1] = Vd . p[n&1]^T ===========================
+        MFB_TACC_INIT(4);  // 0 wait Vd, 1 wait p, 2 wait O free, 3 issue
         for (int n = 0; n < nb; ++n) {
             const int buf = n & 1;
             const uint32_t u = n >> 1;
             const int vb = NVD == 2 ? buf : 0;
+            MFB_TACC(3);
             bar_sync(TcNamed::kVdFull + vb, kHandoffThreads);  // the 4 V decode warps have stored block n
+            MFB_TACC(0);
             bar_sync(TcNamed::kPFull + buf, kHandoffThreads);  // the 4 epilogue warps have stored p of block n
+            MFB_TACC(1);
             if (lane == 0) {
                 if (u >= 1) mbar_wait(&bars[TcBars::kOEmpty + buf], (u - 1) & 1);
+                MFB_TACC(2);
                 tc_fence_after();
                 const uint32_t a_lo = umma_desc_lo(vd_addr + vb * kDenseBytes, kLboV), b_lo = umma_desc_lo(pb_addr + buf * kPbBytes, 128);
 #pragma unroll
@@ -998,6 +1004,8 @@ __device__ __forceinline__ void compressed_split_tc(const DecodeArgs& a, uint8_t
             }
             __syncwarp();
         }
+        MFB_TACC(3);
+        MFB_TACC_STORE(29, 3, lane == 0);  // slots 29 (wait Vd), 30 (wait p), 31 (wait O free)
         if (lane == 0) {
             for (int j = nb > 2 ? nb - 2 : 0; j < nb; ++j) {
                 if (NVD == 2 || j == nb - 1) {
@@ -1034,10 +1042,12 @@ __device__ __forceinline__ void compressed_split_tc(const DecodeArgs& a, uint8_t
 #pragma unroll
             for (int g = 0; g < G; ++g) o_acc[g] = fmaf(o_acc[g], cr[g], o[g]);
         };
+        MFB_TACC_INIT(3);  // 0 wait for S / O, 1 load + maxima, 2 second barrier + exp + publish
         for (int n = 0; n < nb; ++n) {
             const int buf = n & 1;
             const uint32_t u = n >> 1;
             const float mk = (mask && valid) ? __half2float(mask[(blk0 + n) * kBlockTokens + t]) : 0.f;
+            MFB_TACC(2);
             if (ew == 0) {
                 mbar_wait(&bars[TcBars::kSFull + buf], u & 1);
                 if (u >= 1) {
@@ -1046,6 +1056,7 @@ __device__ __forceinline__ void compressed_split_tc(const DecodeArgs& a, uint8_t
                 }
             }
             bar_sync(TcNamed::kEpi, 128);
+            MFB_TACC(0);
             tc_fence_after();
             float s[8];
             tmem_ld8(tlane + 8 * buf, s);
@@ -1062,6 +1073,7 @@ __device__ __forceinline__ void compressed_split_tc(const DecodeArgs& a, uint8_t
                 for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                 if (lane == 0) wred[(buf * 8 + g) * 4 + ew] = mx;
             }
+            MFB_TACC(1);
             bar_sync(TcNamed::kEpi, 128);  // the four warps' block maxima are in wred; every warp has read S[buf] and O[buf]
             if (ew == 0 && lane == 0) {
                 mbar_arrive_cta(&bars[TcBars::kSEmpty + buf]);
@@ -1088,6 +1100,8 @@ __device__ __forceinline__ void compressed_split_tc(const DecodeArgs& a, uint8_t
             __syncwarp();
             bar_arrive(TcNamed::kPFull + buf, kHandoffThreads);
         }
+        MFB_TACC(2);
+        MFB_TACC_STORE(24, 3, ew == 0 && lane == 0);
         // the last two blocks' outputs: block nb-2 (rescaled by corr of nb-2 ... see below) then nb-1
         for (int j = nb > 2 ? nb - 2 : 0; j < nb; ++j) {
             if (ew == 0) mbar_wait(&bars[TcBars::kOFull + (j & 1)], (j >> 1) & 1);
@@ -1138,6 +1152,7 @@ __device__ __forceinline__ void compressed_split_tc(const DecodeArgs& a, uint8_t
             const bool single = is_v && NVD == 1;  // one dense buffer, used by every block
             int s = 0;
             uint32_t par = 0;
+            MFB_TACC_INIT(4);  // 0 wait TMA, 1 records, 2 wait dense buffer, 3 decode
             for (int n = 0; n < nb; ++n, ++s) {
                 if (s == D) {
                     s = 0;
@@ -1148,12 +1163,16 @@ __device__ __forceinline__ void compressed_split_tc(const DecodeArgs& a, uint8_t
                 const bool fits = (seg[n * 4 + 4] - sg0) * 4u <= static_cast<uint32_t>(a.slot_nz_bytes);
                 const uint8_t* gblk = nz_g + static_cast<uint64_t>(sg0) * 4u;
                 const uint32_t nz_addr = (fits ? smem_u32(sl + 1024) : 0u) + (seg[n * 4 + w] - sg0) * 4u;
+                MFB_TACC(3);
                 mbar_wait(&bars[full0 + s], par);
+                MFB_TACC(0);
                 build_records(reinterpret_cast<const uint64_t*>(sl) + w * 32, nz_addr, rec);
                 __syncwarp();
+                MFB_TACC(1);
                 const int db = single ? 0 : (n & 1);
                 const uint32_t ud = single ? static_cast<uint32_t>(n) : static_cast<uint32_t>(n >> 1);
                 if (ud >= 1) mbar_wait(&bars[dempty0 + db], (ud - 1) & 1);  // the MMAs that read this dense buffer last are done
+                MFB_TACC(2);
                 if (fits) decode_to_umma32<true>(my_rec, lc, gblk, dst0 + db * kDenseBytes, lbo);
                 else decode_to_umma32<false>(my_rec, lc, gblk, dst0 + db * kDenseBytes, lbo);
                 fence_async_smem();  // this lane's dense stores -> visible to the tensor core's (async proxy) reads
@@ -1165,6 +1184,8 @@ __device__ __forceinline__ void compressed_split_tc(const DecodeArgs& a, uint8_t
                 if (is_v && tid == kWarpV0 * 32 && n == 0) MFB_TRACE_AT(6);
                 if (is_v && tid == kWarpV0 * 32 && n == nb - 1) MFB_TRACE_AT(7);
             }
+            MFB_TACC(3);
+            MFB_TACC_STORE(is_v ? 20 : 16, 4, lane == 0 && w == 0);
         };
         if (warp >= kWarpV0) decode_role(std::true_type{});
         else decode_role(std::false_type{});
