@@ -53,6 +53,11 @@ constexpr int kTcThreads = kTcWarps * 32;  // 480
 constexpr int kWarpEpi0 = 8, kWarpProducerTc = 12, kWarpMmaS = 13, kWarpMmaO = 14;
 constexpr bool use_tc(int G) { return MFB_GQA_TC != 0 && G >= 4; }
 constexpr int cta_threads(int G) { return use_tc(G) ? kTcThreads : kAttnThreads; }
+#ifndef MFB_G4_CTAS
+#define MFB_G4_CTAS 2  // 3 (64 registers, a few spills) measured 5-12 % slower on the config 3 / 5 shapes
+#endif
+// resident CTAs per SM each instantiation is compiled for (register cap) and planned with
+constexpr int ctas_per_sm(int G) { return G <= 1 ? MFB_G1_CTAS : (G == 2 ? 2 : (G == 4 ? (use_tc(G) ? 2 : MFB_G4_CTAS) : 1)); }
 constexpr int kWinWarps = 8;                   // warps used by the dense-window path
 constexpr int kWinThreads = kWinWarps * 32;
 constexpr int kChunk = 16;                     // tiles per operand-register chunk
@@ -105,7 +110,7 @@ struct NamedBars {
 constexpr int kHandoffThreads = (kTileWarps + 1) * 32;
 
 struct SmemMap {
-    uint32_t slots_k, slots_v, bars, rec, qs, spart, ps, corr, stat, segk, segv, dense, total;
+    uint32_t slots_k, slots_v, bars, rec, qs, spart, ps, corr, stat, segk, segv, total;
 };
 
 __host__ __device__ inline SmemMap smem_map(int G, int slot_nz_bytes, int depth) {
@@ -119,12 +124,12 @@ __host__ __device__ inline SmemMap smem_map(int G, int slot_nz_bytes, int depth)
     o += ((Bars::kCount * 8 + 15) / 16) * 16;
     m.rec = o;  // uint2 [8 consumer warps][32 tiles][2]
     o += 2 * kTileWarps * 64 * 8;
-    m.qs = o;  // half [128][G]  (G >= 4: [G][kQPitch], channels contiguous)
-    o += (G >= 4 ? G * kQPitch : kHeadDim * G) * 2;
+    m.qs = o;  // half [128][G]  (G >= 4: 32 operand blocks of 4 channels, gqa_mma.cuh)
+    o += G >= 4 ? 32 * oper_block_bytes(G) : kHeadDim * G * 2;
     m.spart = o;  // float [2][4 warps][G][sp_pitch]; reused for the final cross-warp reduction of o
     o += 2 * kTileWarps * G * (G >= 4 ? kTcRowPitch : 64) * 4;
-    m.ps = o;  // half [2][64][G]  (G >= 4: [2][G][kTcRowPitch], token pairs contiguous)
-    o += 2 * (G >= 4 ? kTcRowPitch : 64) * G * 2;
+    m.ps = o;  // half [2][64][G]  (G >= 4: [2][16 operand blocks of 4 tokens])
+    o += G >= 4 ? 2 * 16 * oper_block_bytes(G) : 2 * 64 * G * 2;
     m.corr = o;  // float [2][8]
     o += 2 * 8 * 4;
     m.stat = o;  // float m[8], l[8]; uint32 tag
@@ -133,8 +138,6 @@ __host__ __device__ inline SmemMap smem_map(int G, int slot_nz_bytes, int depth)
     o += (kMaxBlocksPerSplit * 4 + 4) * 4;
     m.segv = o;
     o += (kMaxBlocksPerSplit * 4 + 4) * 4;
-    m.dense = o;  // G >= 4: 64 bytes of zeros, the B fragment of the lanes that are not live in an MMA (gqa_mma.cuh)
-    if (G >= 4) o += 64;
     m.total = o;
     return m;
 }
@@ -532,8 +535,11 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     {
         const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
         if constexpr (G >= 4) {
-            for (int i = tid; i < G * kHeadDim; i += blockDim.x) qs[(i >> 7) * kQPitch + (i & 127)] = q[i];
-            if (tid < 16) reinterpret_cast<uint32_t*>(smem + sm.dense)[tid] = 0u;
+            constexpr int BH = oper_block_bytes(G) / 2;  // halves per operand block
+            for (int i = tid; i < G * kHeadDim; i += blockDim.x) qs[((i & 127) >> 2) * BH + (i >> 7) * 4 + (i & 3)] = q[i];
+            // the zero rows of the q blocks and of both p buffers (64 + 32 blocks, 8 bytes each)
+            for (int i = tid; i < 32 + 2 * 16; i += blockDim.x)
+                *reinterpret_cast<uint2*>((i < 32 ? qs + i * BH : ps + (i - 32) * BH) + G * 4) = make_uint2(0u, 0u);
         } else {
             for (int i = tid; i < G * kHeadDim; i += blockDim.x) qs[(i & 127) * G + (i >> 7)] = q[i];
         }
@@ -563,8 +569,11 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         // =========================== online softmax ===========================
         // Head-parallel lane mapping: 32/G lanes per query head, each lane owns 2G consecutive tokens of the
         // block, so all G heads reduce at once with log2(32/G) shuffle steps (the result gates the V warps).
+        // G >= 4: a lane's 2G tokens are chunks of 4 (chunk c = tokens 4*li + 4*LPH*c ..+3): a chunk is one 16-byte read of
+        // the partial scores (conflict-free across the lanes of a head) and one 8-byte operand-block row of p.
         constexpr int LPH = 32 / G, TPL = 2 * G;
-        const int hg = lane / LPH, t0 = (lane % LPH) * TPL;
+        const int hg = lane / LPH, li = lane % LPH, t0 = li * TPL;
+        auto tok = [&](int i) { return G >= 4 ? 4 * li + 4 * LPH * (i >> 2) + (i & 3) : t0 + i; };
         const bool ref_round = (p.flags & MFB200_F_REF_SCORE_ROUNDING) != 0;
         const __half* mask = p.mask ? static_cast<const __half*>(p.mask) + static_cast<int64_t>(b) * p.mask_stride : nullptr;
         float m_run = -INFINITY, l_run = 0.f;
@@ -572,21 +581,33 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             const int buf = n & 1;
             float mk[TPL];
 #pragma unroll
-            for (int i = 0; i < TPL; ++i) mk[i] = mask ? __half2float(mask[(blk0 + n) * kBlockTokens + t0 + i]) : 0.f;
+            for (int i = 0; i < TPL; ++i) mk[i] = mask ? __half2float(mask[(blk0 + n) * kBlockTokens + tok(i)]) : 0.f;
             bar_sync(NamedBars::kScFull + buf, kHandoffThreads);  // the 4 K warps' partial scores of block n
             float sc[TPL];
 #pragma unroll
             for (int i = 0; i < TPL; ++i) sc[i] = 0.f;
             constexpr int SPP = G >= 4 ? kTcRowPitch : 64;  // row pitch of the partial-score buffer
-            const float* sp = spart + buf * kTileWarps * G * SPP + hg * SPP + t0;
+            const float* sp = spart + buf * kTileWarps * G * SPP + hg * SPP;
 #pragma unroll
-            for (int w = 0; w < kTileWarps; ++w)
+            for (int w = 0; w < kTileWarps; ++w) {
+                if constexpr (G >= 4) {
 #pragma unroll
-                for (int i = 0; i < TPL; i += 2) {
-                    const float2 t = *reinterpret_cast<const float2*>(sp + w * G * SPP + i);
-                    sc[i] += t.x;
-                    sc[i + 1] += t.y;
+                    for (int i = 0; i < TPL; i += 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(sp + w * G * SPP + tok(i));
+                        sc[i] += t.x;
+                        sc[i + 1] += t.y;
+                        sc[i + 2] += t.z;
+                        sc[i + 3] += t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < TPL; i += 2) {
+                        const float2 t = *reinterpret_cast<const float2*>(sp + w * G * SPP + t0 + i);
+                        sc[i] += t.x;
+                        sc[i + 1] += t.y;
+                    }
                 }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[Bars::kScEmpty + buf]);
             float mx = -INFINITY;
@@ -611,20 +632,24 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             l_run = l_run * cr + sum;
             m_run = m_new;
             if (n >= 2) bar_sync(NamedBars::kPEmpty + buf, kHandoffThreads);  // V warps are done with p of block n-2
-            if constexpr (G >= 4) {  // tensor-core variant: p as [g][64 tokens] (A-fragment pairs are along tokens)
-                __half* pb = ps + (buf * G + hg) * kTcRowPitch + t0;
+            if constexpr (G >= 4) {  // p as operand blocks: block = 4 tokens, row hg = this head's 4 probabilities
+                constexpr int BH = oper_block_bytes(G) / 2;
 #pragma unroll
-                for (int i = 0; i < TPL; i += 2) *reinterpret_cast<__half2*>(pb + i) = __floats2half2_rn(sc[i], sc[i + 1]);
+                for (int i = 0; i < TPL; i += 4) {
+                    const __half2 lo = __floats2half2_rn(sc[i], sc[i + 1]), hi = __floats2half2_rn(sc[i + 2], sc[i + 3]);
+                    *reinterpret_cast<uint2*>(ps + (buf * 16 + (tok(i) >> 2)) * BH + hg * 4) =
+                        make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                }
             } else {
                 __half* pb = ps + buf * 64 * G + t0 * G + hg;
 #pragma unroll
                 for (int i = 0; i < TPL; ++i) pb[i * G] = __float2half_rn(sc[i]);
             }
-            if (t0 == 0) corr[buf * 8 + hg] = cr;
+            if (li == 0) corr[buf * 8 + hg] = cr;
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[Bars::kPFull + buf]);
         }
-        if (t0 == 0) {
+        if (li == 0) {
             stat[hg] = m_run;
             stat[8 + hg] = l_run;
         }
@@ -643,7 +668,12 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         // G >= 4: per-lane constants of the block-diagonal HMMA scheme (gqa_mma.cuh)
         [[maybe_unused]] GqaLane<(G >= 4 ? G : 4)> gl;
         if constexpr (G >= 4) gl = make_gqa_lane<G>();
-        [[maybe_unused]] const uint32_t zeros_addr = smem_u32(smem + sm.dense);
+        // byte offset of this lane's B fragment inside an operand block, per MMA: its head's row where it is live, else the zero row
+        [[maybe_unused]] uint32_t oper_row[G >= 4 ? G / 2 : 1];
+        if constexpr (G >= 4) {
+#pragma unroll
+            for (int m = 0; m < G / 2; ++m) oper_row[m] = 8u * (gl.live_m == static_cast<uint32_t>(m) ? gl.g_live : static_cast<uint32_t>(G));
+        }
         int s = 0;
         uint32_t par = 0;
         for (int n = 0; n < nb; ++n, ++s) {
@@ -672,7 +702,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                     uint32_t oper[NM];
 #pragma unroll
                     for (int m = 0; m < NM; ++m)
-                        oper[m] = gl.live_m == static_cast<uint32_t>(m) ? smem_u32(qs + gl.g_live * kQPitch + 32 * w) : zeros_addr;
+                        oper[m] = smem_u32(qs) + 8 * w * oper_block_bytes(G) + oper_row[m];
                     if (fits) tiles32_mma<G, true>(my_rec, lc, gblk, oper, acc);
                     else tiles32_mma<G, false>(my_rec, lc, gblk, oper, acc);
                     __syncwarp();
@@ -702,8 +732,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                     uint32_t oper[NM];
 #pragma unroll
                     for (int m = 0; m < NM; ++m)
-                        oper[m] = gl.live_m == static_cast<uint32_t>(m) ? smem_u32(ps + (buf * G + gl.g_live) * kTcRowPitch + 32 * (w & 1))
-                                                                        : zeros_addr;
+                        oper[m] = smem_u32(ps) + (buf * 16 + 8 * (w & 1)) * oper_block_bytes(G) + oper_row[m];
                     if (fits) tiles32_mma<G, true>(my_rec, lc, gblk, oper, gq_o);
                     else tiles32_mma<G, false>(my_rec, lc, gblk, oper, gq_o);
                     __syncwarp();
@@ -1397,7 +1426,7 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
 // flagged merge.  (The uniform kernels carry no segment-loop state in registers; the ticket kernels carry none of
 // the flagged protocol's code: sharing instantiations cost 2-3 % through register pressure.)
 template <int G, int MODE>
-__global__ void __launch_bounds__(cta_threads(G), (G <= 1 ? MFB_G1_CTAS : (G <= 4 ? 2 : 1))) sparse_decode_attn_kernel(const __grid_constant__ DecodeArgs a) {
+__global__ void __launch_bounds__(cta_threads(G), ctas_per_sm(G)) sparse_decode_attn_kernel(const __grid_constant__ DecodeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     // 1-D grid, long CTAs first: all compressed splits of all units, then the short window splits.
 #ifdef MFB_POISON
@@ -1481,7 +1510,18 @@ static int pick_slot_nz_bytes(const mfb200_decode_params* p) {
     return kb * 1024;
 }
 
-static int pick_depth(int slot_nz_bytes) { return slot_nz_bytes <= 8 * 1024 ? 3 : 2; }
+// Ring geometry of the CUDA-core / mma.sync variants: the plan counts on ctas_per_sm(G) resident CTAs per SM, so the
+// shared memory of one CTA has to fit that many times (228 KB per SM, 1 KB reserved per CTA).  Depth 3 for small slots
+// when it fits, else depth 2; a slot that still does not fit is cut (the rare block that is larger than its slot takes
+// the kernel's global-load path instead).
+static void fit_ring(int G, int* slot_nz_bytes, int* depth) {
+    const int budget = 233472 / ctas_per_sm(G) - 1024;
+    int slot = *slot_nz_bytes;
+    const int d = (slot <= 8 * 1024 && static_cast<int>(smem_map(G, slot, 3).total) <= budget) ? 3 : 2;
+    while (slot > 1024 && static_cast<int>(smem_map(G, slot, d).total) > budget) slot -= 1024;
+    *slot_nz_bytes = slot;
+    *depth = d;
+}
 
 template <int G, int MODE>
 static int launch_decode(const DecodeArgs& a, cudaStream_t s) {
@@ -1528,7 +1568,7 @@ static Plan make_plan(int batch, int kv_heads, int groups, int comp_len, int win
     const int64_t units = static_cast<int64_t>(batch) * kv_heads;
     const int nblk = comp_len / kBlockTokens;
     if (nblk > 0) {
-        const int64_t slots = static_cast<int64_t>(sm_count) * (groups <= 1 ? MFB_G1_CTAS : (groups <= 4 ? 2 : 1));
+        const int64_t slots = static_cast<int64_t>(sm_count) * ctas_per_sm(groups);
         // No slots are held back for the window CTAs: they are short, trail the compressed CTAs in the grid and take
         // the slots of the first compressed CTAs that finish (a reserve of up to slots/8 measured 2 % slower at batch 1).
         const int64_t avail = slots;
@@ -1758,7 +1798,7 @@ extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb
                     p->workspace_kb, need);
     }
     a.slot_nz_bytes = pick_slot_nz_bytes(p);
-    a.depth = pick_depth(a.slot_nz_bytes);
+    fit_ring(p->groups, &a.slot_nz_bytes, &a.depth);
     a.nvd = 1;
     if (use_tc(p->groups)) {
         // two CTAs per SM: 227 KB / 2 minus the per-CTA reservation.  Ring depth 2 (the dense operand buffers are the

@@ -15,7 +15,7 @@
 //       and D[gid+8][...] the same for its odd position: 4 tiles x 64 positions x G heads per G/2 MMAs, no shuffles.
 //   Thread (gid, tig) holds B[k in K_tig][n = 8m + gid] of MMA m: non-zero only if tig == jq(n), i.e. a lane is "live"
 //       in at most ONE of the G/2 MMAs, where its fragment is 8 contiguous bytes operand[g][4 tiles]; in the others it
-//       reads 8 bytes of a zero block (one LDS.64 per MMA either way: 5 distinct addresses, one wavefront).
+//       reads the zero row of the same operand block (one LDS.64 per MMA either way, one wavefront).
 //
 // Per 64-position tile this costs LDS.64 record, LOP3, POPC, IMAD, 2 x LOP3->P, 2 x predicated LDS.U16 (into zeroed
 // registers), PRMT, plus per 4 tiles G/2 x (LDS.64 + HMMA): ~10.5 instructions and ~3.5 shared-memory
@@ -30,9 +30,11 @@
 
 namespace mfb {
 
-constexpr int kTcRowPitch = 72;  // elements per [g] row of the score / probability buffers of the G >= 4 variants (64 + 8)
-constexpr int kQPitch = 136;     // halves per [g] row of q in shared memory (128 + 8: the live lanes' 8-byte reads of the
-                                 // 4..8 rows fall into different banks)
+constexpr int kTcRowPitch = 72;  // floats per [g] row of the partial-score buffers of the G >= 4 variants (64 + 8)
+// Operand blocks: the B fragments of one 4-tile group sit in ONE aligned block, row g = operand[g][4 tiles] (8 bytes), row G
+// = zeros (what the lanes that are not live in an MMA read).  An LDS.64 whose 5..9 distinct addresses share a 128-byte
+// line costs one wavefront; the same rows 144 bytes apart cost 2.4 (tools/ubench.cu, profiles/r2_ubench_lds.txt).
+__host__ __device__ constexpr int oper_block_bytes(int G) { return G <= 4 ? 64 : 128; }
 
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -111,9 +113,9 @@ __device__ __forceinline__ void decode_group4(const uint2* rec, const LaneConst&
     a[3] = __byte_perm(y[2], y[3], 0x5410);
 }
 
-// acc[m] += (the warp's 32 tiles) x operand.  oper[m] = shared address this lane reads its B fragment of MMA m from:
-// operand[g_live][first of the 32 tiles] in the MMA it is live in, a 64-byte block of zeros in the others (a plain load
-// per MMA and group - no predicates, no register that would have to survive as "never written").
+// acc[m] += (the warp's 32 tiles) x operand.  oper[m] = shared address this lane reads its B fragment of MMA m from, in
+// the operand block of the warp's first 4-tile group: row g_live in the MMA it is live in, the zero row in the others
+// (a plain load per MMA and group - no predicates, no register that would have to survive as "never written").
 template <int G, bool NZ_SHARED>
 __device__ __forceinline__ void tiles32_mma(const uint2* rec, const LaneConst& lc, const uint8_t* gbase,
                                             const uint32_t (&oper)[G / 2], float (&acc)[G / 2][4]) {
@@ -124,7 +126,7 @@ __device__ __forceinline__ void tiles32_mma(const uint2* rec, const LaneConst& l
         decode_group4<NZ_SHARED>(rec + 8 * grp, lc, gbase, a);
         uint2 bfr[NM];
 #pragma unroll
-        for (int m = 0; m < NM; ++m) bfr[m] = lds_u64(oper[m] + 8 * grp);
+        for (int m = 0; m < NM; ++m) bfr[m] = lds_u64(oper[m] + oper_block_bytes(G) * grp);
 #pragma unroll
         for (int m = 0; m < NM; ++m) mma16816(acc[m], a, bfr[m]);
     }

@@ -84,6 +84,20 @@ __global__ void lds_shape(uint32_t* out, uint32_t seed) {
             if (MODE == 5) { uint4 v = *reinterpret_cast<uint4*>(&sm[base + 4 * (lane >> 4)]); acc += v.x ^ v.y ^ v.z ^ v.w; }  // LDS.128, 2 addr
             if (MODE == 6) acc += reinterpret_cast<uint16_t*>(sm)[2 * base + lane + (lane >> 2)];  // LDS.U16, ~40 consecutive halves
             if (MODE == 7) acc += sm[base + lane];                                                // LDS.32, 32 consecutive words
+            // B-fragment shapes of the GQA HMMA path: 16 live lanes read one of 4 rows (g = gid % 4), 16 dead lanes a zero block
+            if (MODE >= 8 && MODE <= 13) {
+                const uint32_t gid = lane >> 2, tig = lane & 3;
+                const bool live = (tig & 1) == (gid >> 2);
+                uint32_t w;  // word index
+                if (MODE == 8 || MODE == 10 || MODE == 12) w = live ? base + 36 * (gid & 3) : (base + 1024 + 6) & 2047;   // rows 144 B apart, zeros elsewhere
+                else w = (base & ~15u) + (live ? 2 * (gid & 3) : 8);                                            // 4 rows + zeros inside one 64-byte block
+                if (MODE <= 9) { uint2 v = *reinterpret_cast<uint2*>(&sm[w & ~1u]); acc += v.x ^ v.y; }
+                else if (MODE <= 11) acc += sm[w];
+                else if (tig < 2 ? live : false) { uint2 v = *reinterpret_cast<uint2*>(&sm[w & ~1u]); acc += v.x ^ v.y; }  // predicated: 8 lanes
+            }
+            if (MODE == 14) { uint4 v = make_uint4(acc, lane, it, i); *reinterpret_cast<uint4*>(&sm[(off + 4 * lane) & 2047]) = v; }       // STS.128 contiguous
+            if (MODE == 15) { uint2 v = make_uint2(acc, lane); *reinterpret_cast<uint2*>(&sm[(off + 4 * lane) & 2047]) = v;
+                              *reinterpret_cast<uint2*>(&sm[(off + 4 * lane + 2) & 2047]) = v; }                                           // 2 x STS.64, 16-byte lane stride
         }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
@@ -122,6 +136,14 @@ int main() {
     run_lds<5>("LDS.128 2 addr (half-warps)");
     run_lds<6>("LDS.U16 ~40 consecutive");
     run_lds<7>("LDS.32 32 consecutive");
+    run_lds<8>("LDS.64 B-frag rows 144B apart");
+    run_lds<9>("LDS.64 B-frag in one 64B block");
+    run_lds<10>("LDS.32 B-frag rows 144B apart");
+    run_lds<11>("LDS.32 B-frag in one 64B block");
+    run_lds<12>("@P LDS.64 8 lanes rows apart");
+    run_lds<13>("@P LDS.64 8 lanes one block");
+    run_lds<14>("STS.128 contiguous");
+    run_lds<15>("2 x STS.64 16B lane stride");
     run<0>("popc+iadd", 1);
     run<1>("flo(clz)+iadd", 1);
     run<2>("brev+iadd", 1);
