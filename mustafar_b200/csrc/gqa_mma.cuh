@@ -34,6 +34,10 @@ constexpr int kTcRowPitch = 72;  // floats per [g] row of the partial-score buff
 // Operand blocks: the B fragments of one 4-tile group sit in ONE aligned block, row g = operand[g][4 tiles] (8 bytes), row G
 // = zeros (what the lanes that are not live in an MMA read).  An LDS.64 whose 5..9 distinct addresses share a 128-byte
 // line costs one wavefront; the same rows 144 bytes apart cost 2.4 (tools/ubench.cu, profiles/r2_ubench_lds.txt).
+#ifndef MFB_GQA_UNROLL
+#define MFB_GQA_UNROLL 8  // fully unrolled: the next group's record loads overlap this group's value loads (2 -> 8: -5..7 %)
+#endif
+constexpr int kGqaUnroll = MFB_GQA_UNROLL;  // 4-tile groups decoded per loop body
 __host__ __device__ constexpr int oper_block_bytes(int G) { return G <= 4 ? 64 : 128; }
 
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
@@ -116,11 +120,12 @@ __device__ __forceinline__ void decode_group4(const uint2* rec, const LaneConst&
 // acc[m] += (the warp's 32 tiles) x operand.  oper[m] = shared address this lane reads its B fragment of MMA m from, in
 // the operand block of the warp's first 4-tile group: row g_live in the MMA it is live in, the zero row in the others
 // (a plain load per MMA and group - no predicates, no register that would have to survive as "never written").
+// (Holding the K side's q fragments in 32 registers for the whole split instead measured 2 % slower.)
 template <int G, bool NZ_SHARED>
 __device__ __forceinline__ void tiles32_mma(const uint2* rec, const LaneConst& lc, const uint8_t* gbase,
                                             const uint32_t (&oper)[G / 2], float (&acc)[G / 2][4]) {
     constexpr int NM = G / 2;
-#pragma unroll 2
+#pragma unroll kGqaUnroll
     for (int grp = 0; grp < 8; ++grp) {
         uint32_t a[4];
         decode_group4<NZ_SHARED>(rec + 8 * grp, lc, gbase, a);

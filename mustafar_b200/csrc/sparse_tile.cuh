@@ -7,8 +7,7 @@
 // rank is rank+bit0.  Lanes 0-15 work on the high word (positions 0-31), lanes 16-31 on the low
 // word; a "record" prepared once per tile stores {word, smem byte address of the word's first
 // nonzero} so the inner loop is, per 64 positions,
-//     LDS.64 record, LOP3 (mask), POPC, IMAD (address), 2x LDS.U16, 2x LOP3->predicate, SEL,
-//     2x @p FHFMA
+//     LDS.64 record, LOP3 (mask), POPC, IMAD (address), 2x LDS.U16, 2x LOP3->predicate, 2x @p FHFMA
 // FHFMA is Blackwell's mixed-precision FMA (PTX fma.rn.f32.f16: fp16 x fp16 + fp32 -> fp32, one
 // rounding): the fp16 nonzero and the fp16 operand (q or p) are multiplied without any conversion
 // instruction and accumulated in fp32.
@@ -73,30 +72,50 @@ struct DecodedPair {
     bool b0, b1;
 };
 
+#ifndef MFB_INCL_RANK
+#define MFB_INCL_RANK 1
+#endif
 template <bool NZ_SHARED>
 __device__ __forceinline__ DecodedPair decode_pair(const uint2* rec, const LaneConst& lc, const uint8_t* gbase) {
     const uint2 r = *rec;
     const uint32_t w = r.x;
-    uint32_t addr;  // r.y + 2*rank as one IMAD: keeps the half-rate integer-ALU pipe free
-    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(__popc(w & lc.above)), "r"(r.y));
     DecodedPair d;
     d.b0 = (w & lc.bit0) != 0;
     d.b1 = (w & lc.bit1) != 0;
+#if MFB_INCL_RANK
+    // Rank taken INCLUSIVE of the lane's first position: the second value then sits at that rank and the first one slot
+    // before it - neither load depends on a bit test and no select is needed afterwards.  (Rank 0 with the first bit
+    // clear reads the 2 bytes in front of the group - the bitmap area of the slot -, never used.)
+    uint32_t addr1;  // r.y + 2*rank as one IMAD: keeps the half-rate integer-ALU pipe free
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr1) : "r"(__popc(w & (lc.above | lc.bit0))), "r"(r.y));
     uint32_t x, y;
     if (NZ_SHARED) {
-        // x unconditional: with a clear bit it reads the next value / padding / stale bytes inside our
-        // own shared allocation and is never used.  The second value sits one slot further iff b0.
-        x = lds_u16(addr);
-        y = lds_u16(addr + 2);  // unconditional too: keeps the predicates' live ranges short (see callers)
+        x = lds_u16(addr1 - 2);
+        y = lds_u16(addr1);
     } else {
         // overflow path (block larger than the staging slot): values come straight from global,
-        // predicated so that nothing is read past the end of the buffer.
+        // predicated so that nothing is read outside the buffer.
+        const uint16_t* g = reinterpret_cast<const uint16_t*>(gbase + addr1);
+        x = d.b0 ? g[-1] : 0;
+        y = d.b1 ? g[0] : 0;
+    }
+    d.x = static_cast<uint16_t>(x);
+    d.y = static_cast<uint16_t>(y);
+#else
+    uint32_t addr;
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(__popc(w & lc.above)), "r"(r.y));
+    uint32_t x, y;
+    if (NZ_SHARED) {
+        x = lds_u16(addr);
+        y = lds_u16(addr + 2);
+    } else {
         const uint16_t* g = reinterpret_cast<const uint16_t*>(gbase + addr);
         x = (d.b0 || d.b1) ? g[0] : 0;
         y = (d.b0 && d.b1) ? g[1] : 0;
     }
     d.x = static_cast<uint16_t>(x);
     d.y = static_cast<uint16_t>(d.b0 ? y : x);  // the pair's second value sits one slot further iff b0
+#endif
     return d;
 }
 

@@ -18,8 +18,8 @@ constexpr int kSpmvThreads = 128;
 constexpr int kSpmvWarps = 4;
 
 struct SpmvSmem {
+    __align__(16) uint64_t bmp[kTilesPerBlock];            // first: the decode may read the 2 bytes in front of nz
     __align__(16) uint8_t nz[kTilesPerBlock * kTile * 2];  // worst case 16 KB
-    __align__(16) uint64_t bmp[kTilesPerBlock];
     uint2 rec[kSpmvWarps][64];
     float vec[8 * kHeadDim];            // key: B rows as [c][n]; value: P block as [t][n] (64*8)
     float part[kSpmvWarps][8][64];      // key: per-warp partial scores; value: final cross-warp reduce
