@@ -676,6 +676,10 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
         }
         int s = 0;
         uint32_t par = 0;
+        // (trace build) 0 wait TMA, 1 records, 2 wait softmax (V: p ready; K: score buffer free), 3 tiles + hand-off.
+        // Caveat: BAR.SYNC is DEFER_BLOCKING - a clock read right after it issues before the warp blocks, the wait is
+        // charged to the next phase; mbarrier waits are charged correctly.
+        MFB_TACC_INIT(4);
         for (int n = 0; n < nb; ++n, ++s) {
             if (s == D) {
                 s = 0;
@@ -688,9 +692,12 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             const bool fits = (seg[n * 4 + 4] - sg0) * 4u <= static_cast<uint32_t>(a.slot_nz_bytes);
             const uint8_t* gblk = nz_g + static_cast<uint64_t>(sg0) * 4u;
             const uint32_t nz_addr = (fits ? smem_u32(sl + 1024) : 0u) + (seg[n * 4 + w] - sg0) * 4u;
+            MFB_TACC(3);
             mbar_wait(&bars[full0 + s], par);
+            MFB_TACC(0);
             build_records(reinterpret_cast<const uint64_t*>(sl) + w * 32, nz_addr, rec);
             __syncwarp();
+            MFB_TACC(1);
             if constexpr (G >= 4) {
                 // ---------- G >= 4: register-fragment HMMA, all G heads from one decode (gqa_mma.cuh) ----------
                 constexpr int NM = G / 2;
@@ -707,7 +714,9 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                     else tiles32_mma<G, false>(my_rec, lc, gblk, oper, acc);
                     __syncwarp();
                     bar_arrive(empty0 + s, kHandoffThreads);  // ring slot no longer needed
+                    MFB_TACC(3);
                     mbar_wait(&bars[Bars::kScEmpty + buf], par2 ^ 1);
+                    MFB_TACC(2);
                     float* sp = spart + ((buf * kTileWarps + w) * G + gl.g0) * kTcRowPitch;
 #pragma unroll
                     for (int m = 0; m < NM; ++m) {
@@ -721,6 +730,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                 } else {
                     // out[g][channel] += p[g][token] * V over tokens 32(w&1)..+31: operand = p[g][token]
                     mbar_wait(&bars[Bars::kPFull + buf], par2);
+                    MFB_TACC(2);
                     const float c_lo = corr[buf * 8 + gl.g0], c_hi = corr[buf * 8 + gl.g0 + 1];
 #pragma unroll
                     for (int m = 0; m < NM; ++m) {
@@ -749,7 +759,9 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                 tiles32<G>(fits, my_rec, lc, gblk, qs + (32 * w) * G, sc);
                 __syncwarp();
                 bar_arrive(empty0 + s, kHandoffThreads);
+                MFB_TACC(3);
                 mbar_wait(&bars[Bars::kScEmpty + buf], par2 ^ 1);
+                MFB_TACC(2);
                 float* sp = spart + ((buf * kTileWarps + w) * G) * 64;
 #pragma unroll
                 for (int g = 0; g < G; ++g) *reinterpret_cast<float2*>(sp + g * 64 + 2 * lane) = make_float2(sc[g][0], sc[g][1]);
@@ -760,6 +772,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             } else {
                 // V item: tiles 32w .. 32w+31 = channel half (w>>1), tokens 32*(w&1)+j -> channels (2*lane, 2*lane+1)
                 mbar_wait(&bars[Bars::kPFull + buf], par2);
+                MFB_TACC(2);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     const float c = corr[buf * 8 + g];
@@ -774,6 +787,8 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                 if (tid == kWarpV0 * 32 && n == nb - 1) MFB_TRACE_AT(7);
             }
         }
+        MFB_TACC(3);
+        MFB_TACC_STORE(is_v ? 20 : 16, 4, lane == 0 && w == 0);
     }
     // ---- cross-warp reduction of o: V warps (0,1) hold channel half 0, (2,3) half 1 -------------------
     __syncthreads();

@@ -65,8 +65,7 @@ def main():
                  29: "MMA-O wait Vd", 30: "MMA-O wait p", 31: "MMA-O wait O free"}
     else:
         names = {16: "K wait TMA", 17: "K records", 18: "K wait score buf", 19: "K tiles+handoff", 20: "V wait TMA", 21: "V records",
-                 22: "V wait p", 23: "V tiles+handoff", 24: "S0 wait scores", 25: "S0 load+sum+arrive", 26: "S0 wait p buf", 27: "S0 round+max",
-                 28: "S0 exp", 29: "S0 publish p", 30: "S0 loop top"}
+                 22: "V wait p", 23: "V tiles+handoff"}
     for k_, nm in names.items():
         d = tc[:, k_] / nbk
         print(f"  {nm:18s}: p10 {np.percentile(d, 10):7.0f}  p50 {np.median(d):7.0f}  p90 {np.percentile(d, 90):7.0f} clk/block")
