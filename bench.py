@@ -377,7 +377,7 @@ def run_ours(args):
         "data": "synthetic", "config": config_dict(layers),
         "us_per_layer_step": ms_dev * 1e3 / (K * layers),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "sparse_decode_attn_kernel<4, *> (tcgen05 GQA variant)",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "sparse_decode_attn_kernel<4, *> (GQA variant: register-fragment HMMA with a block-diagonal operand)",
                      "us_per_launch": us_per_launch, "algorithmic_bytes_per_launch": algo_bytes,
                      "frac_of_8TBps_spec": achieved / 8000.0,
                      "how": f"{layers} x K back-to-back launches (one per layer cache of this rank, {bl} sequences each), CUDA events "
@@ -573,6 +573,25 @@ def run_extras(args, world, rank, dev, timed, layer_params, launch_all, K):
     guarded("cfg3_layer", lambda: compare(16, 8, 4, 8192, 0.7, 4, "configs[2] layer: batch 16 x 8 KV heads (G=4) x 8K, s=0.7", True))
     guarded("cfg5_layer", lambda: compare(32, 8, 4, 32768, 0.5, 1, "configs[4] layer (the headline's kernel): batch 32 x 8 KV heads (G=4) x 32K, s=0.5", True))
     guarded("cfg1_compare", lambda: compare(1, 32, 1, 4096, 0.5, 8, "configs[0] layer, cold L2 rotation of 8 caches, vs baselines", True))
+
+    def cfg2_model():
+        """BASELINE configs[1] at model level (tools/model_bench.py, own process): stock transformers Llama-2-7B geometry,
+        random init, 4096 prompt + 1024 generated, this library's cache/attention vs a dense cache + FlashAttention-2."""
+        tmp = os.path.join(ROOT, "gpurun_out", f"model_bench_{os.getpid()}.json")
+        os.makedirs(os.path.dirname(tmp), exist_ok=True)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "model_bench.py"), "--arms", "mustafar,flash", "--json", tmp],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=420)
+        if r.returncode != 0:
+            raise RuntimeError(r.stderr[-300:])
+        res = json.load(open(tmp))
+        os.remove(tmp)
+        arms = {a["arm"]: a for a in res["arms"]}
+        if "decode_tok_s_per_seq" in arms.get("mustafar", {}) and "decode_tok_s_per_seq" in arms.get("flash", {}):
+            res["decode_speedup_vs_dense_flash_attention_2"] = arms["mustafar"]["decode_tok_s_per_seq"] / arms["flash"]["decode_tok_s_per_seq"]
+        return res
+
+    if world == 1 and not os.environ.get("MFB200_BENCH_NO_MODEL"):
+        guarded("cfg2_model", cfg2_model)
     return out
 
 
