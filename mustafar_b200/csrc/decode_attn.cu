@@ -62,7 +62,10 @@ constexpr int kWinWarps = 8;                   // warps used by the dense-window
 constexpr int kWinThreads = kWinWarps * 32;
 constexpr int kChunk = 16;                     // tiles per operand-register chunk
 constexpr int kMaxDepth = 4;
-constexpr int kMaxBlocksPerSplit = 128;
+#ifndef MFB_MAX_BLOCKS
+#define MFB_MAX_BLOCKS 128
+#endif
+constexpr int kMaxBlocksPerSplit = MFB_MAX_BLOCKS;  // blocks of one segment (sizes the segment-offset tables in shared memory)
 constexpr int kMaxBlocksPerSplitTc = 64;  // tcgen05 variant: smaller segment tables (shared memory goes to the dense operand buffers)
 constexpr int kWinTokensPerSplit = 64;
 constexpr int kPartStride = 132;  // {fp32 value, tag} entries per (split, head): o[128], m, l, pad

@@ -16,6 +16,7 @@ CFG = {
     "cfg3": dict(b=16, hkv=8, g=4, t=8192, s=0.7),
     "cfg4s": dict(b=4, hkv=32, g=1, t=32768, s=0.7),   # config 4 at 1/16 of the batch
     "cfg5s": dict(b=4, hkv=8, g=4, t=32768, s=0.5),    # config 5 at 1/8 of the batch
+    "cfg5": dict(b=32, hkv=8, g=4, t=32768, s=0.5),    # config 5, one layer (the bench headline's kernel)
     "mid1": dict(b=8, hkv=32, g=1, t=4096, s=0.5),     # mid-size MHA launches: 256 units
     "mid2": dict(b=32, hkv=8, g=1, t=8192, s=0.7),
     "mid3": dict(b=2, hkv=32, g=1, t=4096, s=0.5),     # 64 units x 60 blocks: 8.6 blocks per CTA slot

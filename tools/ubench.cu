@@ -29,6 +29,11 @@ __global__ void k(uint32_t* out, uint32_t seed) {
             if (OP == 9) a[i] = __ballot_sync(0xffffffffu, a[i] & 1) + a[i];  // VOTE
             if (OP == 10) a[i] = __reduce_add_sync(0xffffffffu, a[i]);   // REDUX
             if (OP == 11) a[i] = (a[i] & 1) ? a[i] >> 1 : seed;           // SEL-ish
+            // pipe-sharing probes: 2 LDS + 1 POPC per iteration (the decode loop's mix), and the same with the POPC replaced by a LOP3
+            if (OP == 12) { uint32_t t = sm[(a[i] >> 7) & 2047]; t += ((const uint16_t*)sm)[(a[i] >> 9) & 4095]; a[i] = __popc(a[i] ^ t) + t; }
+            if (OP == 13) { uint32_t t = sm[(a[i] >> 7) & 2047]; t += ((const uint16_t*)sm)[(a[i] >> 9) & 4095]; a[i] = ((a[i] ^ t) & seed) + t; }
+            if (OP == 14) { uint32_t t = sm[(a[i] >> 7) & 2047]; a[i] = __shfl_xor_sync(0xffffffffu, a[i] + t, 1); }   // 1 LDS + 1 SHFL
+            if (OP == 15) { a[i] = __popc(a[i]) + __shfl_xor_sync(0xffffffffu, a[i], 1); }                              // 1 POPC + 1 SHFL
         }
     }
     uint32_t r = 0;
@@ -156,5 +161,9 @@ int main() {
     run<9>("vote+lop+iadd", 2);
     run<10>("redux.add", 0);
     run<11>("sel-ish", 2);
+    run<12>("2 lds + popc (+3 alu)", 3);
+    run<13>("2 lds + lop (+3 alu)", 3);
+    run<14>("lds + shfl (+2 alu)", 2);
+    run<15>("popc + shfl (+1 alu)", 1);
     return 0;
 }
