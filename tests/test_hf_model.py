@@ -60,14 +60,22 @@ def _masked_dense_cache(sparsity, residual=32):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("hkv,sparsity", [(2, 0.5), (1, 0.7)])
-def test_llama_decode_matches_masked_dense(hkv, sparsity):
-    from transformers import LlamaConfig, LlamaForCausalLM
+@pytest.mark.parametrize("family,heads,hkv,sparsity", [("llama", 2, 2, 0.5), ("llama", 2, 1, 0.7),
+                                                       ("mistral", 4, 1, 0.5)])  # Mistral-7B's 4 query heads per KV head
+def test_llama_decode_matches_masked_dense(family, heads, hkv, sparsity):
+    """Stock Llama and Mistral classes (the reference clones both: llama_mustafar_kernel.py,
+    mistral_mustafar_Kt_Mag_Vt_Mag.py:440-669) through the same cache / attention function."""
     import mustafar_b200.hf as mhf
-    cfg = LlamaConfig(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
-                      num_key_value_heads=hkv, head_dim=128, max_position_embeddings=2048)
+    if family == "llama":
+        from transformers import LlamaConfig as Config, LlamaForCausalLM as Model
+        extra = {}
+    else:
+        from transformers import MistralConfig as Config, MistralForCausalLM as Model
+        extra = {"sliding_window": None}  # Mistral-7B-Instruct-v0.2 attends over the full context
+    cfg = Config(vocab_size=512, hidden_size=128 * heads, intermediate_size=512, num_hidden_layers=2, num_attention_heads=heads,
+                 num_key_value_heads=hkv, head_dim=128, max_position_embeddings=2048, **extra)
     torch.manual_seed(0)
-    model = LlamaForCausalLM(cfg).half().cuda().eval()
+    model = Model(cfg).half().cuda().eval()
     batch, T0, steps = 2, 300, 270  # window 44 -> 288 at T = 544: one compression event inside the run
     ids = torch.randint(0, cfg.vocab_size, (batch, T0 + steps), generator=torch.Generator().manual_seed(1)).cuda()
 
