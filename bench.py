@@ -506,9 +506,36 @@ def run_extras(args, world, rank, dev, timed, layer_params, launch_all, K):
         ms = timed(step, K, sample_clocks=False)
         launch_all(ps)
         ms_nc = timed(lambda i: launch_all(ps), K, sample_clocks=False)
-        return {"workload": f"configs[0]/[1] layer head-partitioned: batch 1, 32 heads / {world} ranks, 4K, s=0.5, 32 layers, "
-                            "attention + NCCL all-gather of [1, 32/N, 1, 128] per layer",
-                "us_per_layer_step_with_all_gather": ms * 1e3 / (K * 32), "us_per_layer_step_attention_only": ms_nc * 1e3 / (K * 32)}
+        res = {"workload": f"configs[0]/[1] layer head-partitioned: batch 1, 32 heads / {world} ranks, 4K, s=0.5, 32 layers; the [1, 32, 1, 128] "
+                           "output of a layer assembled (a) by ONE NCCL all-gather per layer, (b) by the fused launch's peer-to-peer "
+                           "store epilogue into every rank's gathered buffer + one wait launch (no collective)",
+               "us_per_layer_step_with_all_gather": ms * 1e3 / (K * 32), "us_per_layer_step_attention_only": ms_nc * 1e3 / (K * 32)}
+        try:
+            from mustafar_b200.partition import PeerOutput
+            po = PeerOutput(p1, 1, 32, 1, dev)
+            sid = [0]
+
+            def step_peer(_):
+                for p in ps:
+                    p.peer = C.addressof(po.block(sid[0]))  # ps are copies of the caches' parameter blocks
+                    attn(C.byref(p), sp)
+                    po.wait(sid[0])
+                    sid[0] += 1
+
+            step_peer(0)
+            torch.cuda.synchronize()
+            want = gather_heads(p1, os_[-1])
+            res["peer_stores_equal_all_gather"] = bool(torch.equal(po.gathered(sid[0] - 1), want))
+            ms_p = timed(step_peer, K, sample_clocks=False)
+            res["us_per_layer_step_with_peer_stores"] = ms_p * 1e3 / (K * 32)
+            res["peer_wait_timed_out"] = po.timed_out()
+            for p in ps:
+                p.peer = None
+            torch.cuda.synchronize()
+            po.close()
+        except Exception as e:  # noqa: BLE001
+            res["peer_stores_error"] = f"{type(e).__name__}: {e}"[:200]
+        return res
     guarded("cfg1_layer", cfg1)
 
     if world > 1 or rank != 0:

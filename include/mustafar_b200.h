@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MFB200_ABI_VERSION 2
+#define MFB200_ABI_VERSION 3
 
 #define MFB200_OK 0
 #define MFB200_EINVAL (-1)  /* bad argument (shape, alignment, null pointer) */
@@ -133,6 +133,23 @@ int mfb200_value_formulation(mfb200_stream_t stream, const void* A, const uint64
 size_t mfb200_value_workspace_bytes(int K_Global, int Batch_Size);
 
 /* ---- fused sparse decode attention ------------------------------------------------------------------ */
+/* Head-sharded decode without a collective: every rank's launch stores its output rows straight into the gathered
+ * output buffer of EVERY rank (peer-to-peer stores over NVLink / NVSwitch from the split-merge epilogue) and then raises
+ * one arrival flag per (rank, unit) on every rank; mfb200_peer_wait() on the consumer side replaces the all-gather.
+ * Replaces the torch.cat / all-gather a tensor-sharded caller would issue after the attention op.  All pointers are
+ * device pointers valid on THIS device (own allocations, or peers' allocations opened with mfb200_ipc_open). */
+#define MFB200_MAX_PEERS 8
+typedef struct mfb200_peer_out {
+    int32_t n_peers;    /* ranks that share the gathered output, 2..MFB200_MAX_PEERS */
+    int32_t rank;       /* this rank */
+    int32_t row0;       /* first row (query head) of this rank inside a sequence's rows_total rows */
+    int32_t rows_total; /* rows (query heads) per sequence of the gathered output: fp16 [B, rows_total, 128] */
+    uint32_t epoch;     /* the flags are set to this value; must grow from launch to launch on the same flags */
+    int32_t reserved;   /* must be 0 */
+    void* out[MFB200_MAX_PEERS];       /* out[r]: rank r's gathered output buffer */
+    uint32_t* flags[MFB200_MAX_PEERS]; /* flags[r]: rank r's arrival flags, uint32 [n_peers][B * Hkv] (zero before first use) */
+} mfb200_peer_out;
+
 typedef struct mfb200_decode_params {
     /* geometry */
     int32_t batch;        /* B  */
@@ -185,6 +202,8 @@ typedef struct mfb200_decode_params {
     /* scratch: >= mfb200_decode_plan() bytes; the counter part must be zero before the first launch
      * (kernels leave it zeroed). */
     void* workspace;
+    /* optional (host pointer, read at launch): also store the output rows into the peers' gathered buffers; NULL = off */
+    const mfb200_peer_out* peer;
 } mfb200_decode_params;
 
 /* Round q·k to fp16 and divide by score_div in fp16 like the reference glue does
@@ -238,6 +257,19 @@ int mfb200_decode_step_layers(mfb200_decode_params* const* layers, int n_layers,
 /* Workspace size that is sufficient for every (comp_len <= max_comp_len, win_len <= max_win_len), plan_hint 0. */
 size_t mfb200_decode_workspace_max(int batch, int kv_heads, int groups, int max_comp_len, int max_win_len,
                                    int sm_count);
+
+/* ---- peer-to-peer plumbing of the head-sharded path ------------------------------------------------------
+ * mfb200_peer_wait: one small launch that returns (in stream order) once flags[0 .. n) >= epoch, i.e. once every rank's
+ * rows of this step have landed in the local gathered buffer.  It gives up after about two seconds and sets *timed_out
+ * (device int32, may be NULL) instead of hanging the stream when a peer died; once set, later waits return at once.
+ * mfb200_peer_alloc/free: cudaMalloc'ed (IPC-exportable) memory; mfb200_ipc_export/open/close: cudaIpc handles (64 bytes)
+ * so that the ranks of ONE node can map each other's buffers; exchange the handles with any host-side channel. */
+int mfb200_peer_wait(const uint32_t* flags, int n, uint32_t epoch, int32_t* timed_out, mfb200_stream_t stream);
+int mfb200_peer_alloc(size_t bytes, void** ptr);
+int mfb200_peer_free(void* ptr);
+int mfb200_ipc_export(void* ptr, unsigned char handle[64]);
+int mfb200_ipc_open(const unsigned char handle[64], void** ptr);
+int mfb200_ipc_close(void* ptr);
 
 /* ---- window append (new token's k and v rows) ----------------------------------------------------
  * win[u, pos, :] = row[u, :] for K and V; row: fp16 [units, 128]. */

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MFB200_LIB", os.path.join(_HERE, "libmustafar_b200.so"))  # override: A/B builds only
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 LAYOUT_KEY = 0
 LAYOUT_VALUE = 1
 F_REF_SCORE_ROUNDING = 1
@@ -38,6 +38,20 @@ class DecodeParams(C.Structure):
         ("k_new", _vp), ("v_new", _vp),
         ("mask", _vp), ("mask_stride", _i64),
         ("workspace", _vp),
+        ("peer", _vp),
+    ]
+
+
+MAX_PEERS = 8
+
+
+class PeerOut(C.Structure):
+    """Mirror of `mfb200_peer_out` (include/mustafar_b200.h): peer-to-peer output stores of the head-sharded decode."""
+
+    _fields_ = [
+        ("n_peers", C.c_int32), ("rank", C.c_int32), ("row0", C.c_int32), ("rows_total", C.c_int32),
+        ("epoch", C.c_uint32), ("reserved", C.c_int32),
+        ("out", _vp * MAX_PEERS), ("flags", _vp * MAX_PEERS),
     ]
 
 
@@ -63,6 +77,12 @@ SIGNATURES = {
     "mfb200_decode_step_layers": (_i32, [C.POINTER(C.POINTER(DecodeParams)), _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "mfb200_decode_workspace_max": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "mfb200_window_append": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
+    "mfb200_peer_wait": (_i32, [_vp, _i32, C.c_uint32, _vp, _vp]),
+    "mfb200_peer_alloc": (_i32, [C.c_size_t, C.POINTER(_vp)]),
+    "mfb200_peer_free": (_i32, [_vp]),
+    "mfb200_ipc_export": (_i32, [_vp, C.c_char_p]),
+    "mfb200_ipc_open": (_i32, [C.c_char_p, C.POINTER(_vp)]),
+    "mfb200_ipc_close": (_i32, [_vp]),
 }
 
 _lib = None

@@ -385,6 +385,12 @@ class MustafarKVCache:
             p.mask, p.mask_stride = None, 0
         return p
 
+    def set_peer_output(self, peer) -> None:
+        """Head-sharded decode: `peer` = a `_lib.PeerOut` block (partition.PeerOutput keeps it alive and up to date) whose
+        buffers every launch of this cache also stores its output rows into; None switches it off again."""
+        self._peer = peer
+        self._params().peer = C.addressof(peer) if peer is not None else None
+
     def _flags(self) -> int:
         flags = _lib.F_REF_SCORE_ROUNDING if self.ref_score_rounding else 0
         if self.pdl:

@@ -84,6 +84,7 @@ struct DecodeArgs {
     int slot_nz_bytes;  // capacity of a slot's nonzero area (multiple of 1024)
     int depth;          // ring depth per stream (K and V each), 2..4
     int nvd;            // tcgen05 variant: dense V buffers (1 or 2; K always has 2)
+    mfb200_peer_out peer;  // head-sharded decode: copy of *p.peer (n_peers = 0: off)
 };
 
 // barrier indices inside the bars[] array
@@ -343,7 +344,24 @@ __device__ __forceinline__ void merge_unit(const DecodeArgs& a, int unit, int sp
             num += s_red[j * G + g][c] * w;
         }
         const int64_t qh = static_cast<int64_t>(unit) * G + g;  // = b*Hq + h*G + g
-        static_cast<__half*>(p.out)[qh * kHeadDim + c] = __float2half_rn(num / den);
+        const __half hv = __float2half_rn(num / den);
+        static_cast<__half*>(p.out)[qh * kHeadDim + c] = hv;
+        if (a.peer.n_peers > 1) {
+            // head-sharded decode: the same row goes straight into every rank's gathered output (P2P stores over NVLink)
+            const int64_t row = static_cast<int64_t>(unit / p.kv_heads) * a.peer.rows_total + a.peer.row0 + (unit % p.kv_heads) * G + g;
+            for (int r = 0; r < a.peer.n_peers; ++r) static_cast<__half*>(a.peer.out[r])[row * kHeadDim + c] = hv;
+        }
+    }
+    if (a.peer.n_peers > 1) {
+        // arrival flag of (this rank, this unit) on every rank: the CTA's row stores happen-before the barrier, thread 0's
+        // system-scope fence makes them visible to whoever acquires the flag (mfb200_peer_wait on the consumer side)
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            const int64_t slot = static_cast<int64_t>(a.peer.rank) * p.batch * p.kv_heads + unit;
+            for (int r = 0; r < a.peer.n_peers; ++r)
+                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.peer.flags[r] + slot), "r"(a.peer.epoch) : "memory");
+        }
     }
     if (tid == 0) *epoch_ptr(p, unit) = tag;  // the next launch (stream-ordered / after its PDL wait) tags with tag + 1
 }
@@ -1795,6 +1813,17 @@ extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb
                     "decode: k_new/v_new need win_len >= 1 and 16-byte alignment");
     DecodeArgs a;
     a.p = *p;
+    a.peer = mfb200_peer_out{};
+    if (p->peer != nullptr) {
+        const mfb200_peer_out& pe = *p->peer;
+        MFB_REQUIRE(pe.n_peers >= 2 && pe.n_peers <= MFB200_MAX_PEERS && pe.rank >= 0 && pe.rank < pe.n_peers && pe.reserved == 0,
+                    "decode: peer output needs 2..%d peers and a rank inside them", MFB200_MAX_PEERS);
+        MFB_REQUIRE(pe.row0 >= 0 && pe.row0 + p->kv_heads * p->groups <= pe.rows_total, "decode: peer output rows [%d, %d) outside [0, %d)",
+                    pe.row0, pe.row0 + p->kv_heads * p->groups, pe.rows_total);
+        for (int r = 0; r < pe.n_peers; ++r)
+            MFB_REQUIRE(pe.out[r] != nullptr && pe.flags[r] != nullptr, "decode: peer %d has no output buffer / flags", r);
+        a.peer = pe;
+    }
     int sm_count = 0;
     {
         const int rc = current_device_sm_count(&sm_count);

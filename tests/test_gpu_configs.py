@@ -185,3 +185,41 @@ def test_layer_batched_step_equals_per_layer_steps():
             o = bb[l].decode_step(q[l].view(b, hkv * g, 1, 128), kn[l].view(b, hkv, 1, 128), vn[l].view(b, hkv, 1, 128))
             assert torch.equal(o.view(b, hkv * g, 128), out_a[l]), (i, l)
     assert all(x.comp_len == y.comp_len and x.win_len == y.win_len for x, y in zip(a, bb)) and a[0].comp_len == 768
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,hkv,groups", [(2, 4, 1), (4, 8, 4)])
+def test_head_sharded_peer_output_equals_all_gather(world, hkv, groups):
+    """Head-sharded decode without a collective (partition.PeerOutput): every rank's launch stores its rows into all ranks'
+    gathered buffers and raises arrival flags.  All ranks live in ONE process on one GPU here (same kernel code path, no
+    IPC); tools/peer_check.py runs the real thing, one process per GPU over cudaIpc."""
+    from mustafar_b200.attention import MustafarKVCache
+    from mustafar_b200.partition import PeerOutput, make_partition, shard_kv, shard_q
+    b, T, s = 1, 700, 0.5
+    g = torch.Generator().manual_seed(world)
+    k = torch.randn(b, hkv, T, 128, generator=g).half().cuda()
+    v = torch.randn(b, hkv, T, 128, generator=g).half().cuda()
+    parts = [make_partition(b, hkv, world, r) for r in range(world)]
+    assert all(p.mode == "head" for p in parts)
+    caches = []
+    for p in parts:
+        c = MustafarKVCache(b, p.local_kv_heads, groups, T + 300, s, s)
+        c.prefill(shard_kv(p, k).contiguous(), shard_kv(p, v).contiguous())
+        caches.append(c)
+    peers = PeerOutput.local_group(parts, b, hkv * groups, groups, "cuda")
+    for step in range(5):  # more steps than buffers: flags and epochs are reused
+        q = torch.randn(b, hkv * groups, 1, 128, generator=g).half().cuda()
+        kn = torch.randn(b, hkv, 1, 128, generator=g).half().cuda()
+        vn = torch.randn(b, hkv, 1, 128, generator=g).half().cuda()
+        outs = []
+        for p, c, po in zip(parts, caches, peers):
+            po.bind(c, step)
+            outs.append(c.decode_step(shard_q(p, q, groups).contiguous(), shard_kv(p, kn).contiguous(), shard_kv(p, vn).contiguous()))
+        want = torch.cat(outs, dim=1)  # what the all-gather would deliver
+        for po in peers:
+            po.wait(step)
+            assert torch.equal(po.gathered(step), want)
+        torch.cuda.synchronize()
+    assert not any(po.timed_out() for po in peers)
+    for po in peers:
+        po.close()
