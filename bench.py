@@ -600,6 +600,10 @@ def run_extras(args, world, rank, dev, timed, layer_params, launch_all, K):
     guarded("cfg3_layer", lambda: compare(16, 8, 4, 8192, 0.7, 4, "configs[2] layer: batch 16 x 8 KV heads (G=4) x 8K, s=0.7", True))
     guarded("cfg5_layer", lambda: compare(32, 8, 4, 32768, 0.5, 1, "configs[4] layer (the headline's kernel): batch 32 x 8 KV heads (G=4) x 32K, s=0.5", True))
     guarded("cfg1_compare", lambda: compare(1, 32, 1, 4096, 0.5, 8, "configs[0] layer, cold L2 rotation of 8 caches, vs baselines", True))
+    # the MHA kernel where it is byte-bound rather than decode-bound: the time per 64-position tile does not depend on the
+    # sparsity, so the HBM fraction is highest at s = 0.5 and a long context (configs[3]'s geometry at configs[0]'s sparsity)
+    guarded("mha_s05_32k_layer", lambda: compare(8, 32, 1, 32768, 0.5, 1, "MHA layer: batch 8 x 32 heads x 32K, s=0.5 (configs[3] geometry at "
+                                                 "configs[0] sparsity: the kernel's best HBM fraction)", True))
 
     def cfg2_model():
         """BASELINE configs[1] at model level (tools/model_bench.py, own process): stock transformers Llama-2-7B geometry,
