@@ -598,6 +598,24 @@ def run_extras(args, world, rank, dev, timed, layer_params, launch_all, K):
         return res
 
     guarded("cfg3_layer", lambda: compare(16, 8, 4, 8192, 0.7, 4, "configs[2] layer: batch 16 x 8 KV heads (G=4) x 8K, s=0.7", True))
+
+    def gqa_ab():
+        """Same-run A/B of the two GQA contractions on the configs[2] shape (own processes: the library is fixed at first load):
+        the shipped register-fragment HMMA path vs the tcgen05 / TMEM variant (`make tc`), cold-L2 medians of tools/prof_attn.py."""
+        import re
+        res = {}
+        for name, lib_name in (("shipped_hmma_cold_us", "libmustafar_b200.so"), ("tcgen05_variant_cold_us", "libmustafar_b200_tc.so")):
+            lib_path = os.path.join(ROOT, "mustafar_b200", lib_name)
+            if not os.path.exists(lib_path):
+                res[name] = "not built"
+                continue
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "prof_attn.py"), "cfg3", "5"], env=dict(os.environ, MFB200_LIB=lib_path),
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=180)
+            m = re.search(r"cold median ([0-9.]+) us", r.stdout)
+            res[name] = float(m.group(1)) if m else f"failed: {r.stderr[-120:]}"
+        return res
+
+    guarded("cfg3_gqa_ab", gqa_ab)
     guarded("cfg5_layer", lambda: compare(32, 8, 4, 32768, 0.5, 1, "configs[4] layer (the headline's kernel): batch 32 x 8 KV heads (G=4) x 32K, s=0.5", True))
     guarded("cfg1_compare", lambda: compare(1, 32, 1, 4096, 0.5, 8, "configs[0] layer, cold L2 rotation of 8 caches, vs baselines", True))
     # the MHA kernel where it is byte-bound rather than decode-bound: the time per 64-position tile does not depend on the

@@ -569,6 +569,38 @@ print("POISON-OK")
     assert r.returncode == 0 and "POISON-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.gpu
+def test_tcgen05_gqa_variant_still_correct():
+    """The G >= 4 contraction on tcgen05 / TMEM (csrc/gqa_tc.cuh, `make tc`) lost the A/B against the register-fragment HMMA
+    path and is not shipped, but it is kept buildable and correct: same cases, same tolerance, through its own library."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "mustafar_b200", "libmustafar_b200_tc.so")
+    if not os.path.exists(lib):
+        pytest.skip("tcgen05 A/B build not present (make -C mustafar_b200/csrc tc)")
+    code = """
+import sys, torch
+sys.path.insert(0, %r)
+from mustafar_b200.attention import MustafarKVCache
+from oracle import torch_oracle as TO
+for (b, hkv, g, T, s) in [(1, 8, 4, 4160, 0.5), (2, 4, 8, 2112, 0.7), (4, 8, 4, 8192, 0.7)]:
+    gen = torch.Generator(device="cuda").manual_seed(T)
+    k = torch.randn(b, hkv, T, 128, device="cuda", generator=gen).half(); v = torch.randn(b, hkv, T, 128, device="cuda", generator=gen).half()
+    q = torch.randn(b, hkv * g, 1, 128, device="cuda", generator=gen).half()
+    c = MustafarKVCache(b, hkv, g, T + 64, s, s); c.prefill(k, v)
+    L = c.comp_len
+    k[:, :, :L] = TO.prune_rows(k[:, :, :L], s); v[:, :, :L] = TO.prune_rows(v[:, :, :L], s)
+    o = c.attend(q); torch.cuda.synchronize()
+    d = (o.float() - TO.masked_dense_attention(q, k, v).float()).abs()
+    assert d.max().item() <= 2e-3 and d.mean().item() <= 1e-3, (b, hkv, g, T, s, d.max().item())
+print("TC-OK")
+""" % root
+    env = dict(os.environ, MFB200_LIB=lib)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "TC-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 # --------------------------------------------------------------------------- size-independent properties
 def test_properties_full_size_config3_shape():
     """B=16 x 8 KV heads, G=4, T=8192, s=0.7 is too big for the numpy oracle; check structural properties:
