@@ -229,6 +229,44 @@ def test_fused_attention_vs_oracle(b, hkv, groups, T, sparsity):
     assert torch.equal(got, got2)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("groups,mode", [(1, "all"), (4, "all"), (2, "some"), (4, "some"), (8, "some")])
+def test_blocks_larger_than_their_ring_slot(groups, mode):
+    """Tie explosions: rows whose magnitudes are all equal keep EVERY element (`|x| >= k-th smallest`), so a 64-token block
+    carries up to 16 KB of nonzeros - more than the sparsity-sized ring slot.  Such blocks are decoded straight from global
+    memory (the NZ_SHARED = false paths of both the CUDA-core and the HMMA decode); `some` mixes them with normal blocks."""
+    from mustafar_b200.attention import MustafarKVCache
+    b, hkv, T, s = 2, 2, 712, 0.5
+    gen = torch.Generator().manual_seed(groups)
+    k = torch.randn(b, hkv, T, 128, generator=gen).half()
+    v = torch.randn(b, hkv, T, 128, generator=gen).half()
+    sign = lambda: (torch.randint(0, 2, (b, hkv, T, 128), generator=gen) * 2 - 1).half()
+    tie_k, tie_v = sign() * 0.5, sign() * 0.25
+    if mode == "all":
+        k, v = tie_k, tie_v
+    else:  # token blocks 2, 3 and 7 of every head are all-ties, the others are ordinary
+        for blk in (2, 3, 7):
+            k[:, :, 64 * blk: 64 * blk + 64] = tie_k[:, :, 64 * blk: 64 * blk + 64]
+            v[:, :, 64 * blk: 64 * blk + 64] = tie_v[:, :, 64 * blk: 64 * blk + 64]
+    q = torch.randn(b, hkv * groups, 1, 128, generator=gen).half()
+    cache = MustafarKVCache(b, hkv, groups, max_tokens=T + 300, k_sparsity=s, v_sparsity=s)
+    cache.prefill(k.cuda(), v.cuda())
+    L = cache.comp_len
+    assert L == 512 and cache.slot_kb < 16
+    kp, vp = k.numpy().copy(), v.numpy().copy()
+    kp[:, :, :L] = O.prune_rows(kp[:, :, :L], s)
+    vp[:, :, :L] = O.prune_rows(vp[:, :, :L], s)
+    if mode == "all":
+        assert np.count_nonzero(kp[:, :, :L]) == kp[:, :, :L].size  # nothing was pruned
+    got = cache.attend(q.cuda())
+    _check_attention(got, q, kp, vp, L)
+    kn, vn = torch.randn(b, hkv, 1, 128, generator=gen).half(), torch.randn(b, hkv, 1, 128, generator=gen).half()
+    got = cache.decode_step(q.cuda(), kn.cuda(), vn.cuda())
+    kp, vp = np.concatenate([kp, kn.numpy()], 2), np.concatenate([vp, vn.numpy()], 2)
+    _check_attention(got, q, kp, vp, L)
+    cache.check_overflow()
+
+
 def _random_geometries(n, seed):
     """Seeded sweep over the planner's regimes: more units than CTA slots, ragged per-unit splits, the boundary
     between the flagged and the ticket merge (16 blocks per compressed CTA), tiny and full windows, every G."""
