@@ -8,7 +8,10 @@ Slots: 0 entry, 1 idx+barriers ready, 2 PDL wait passed, 3 q staged, 4/5 K warp 
 6/7 V warp first/last block done, 8 roles joined, 9 partial published / ticket taken, 10 exit, 11 smid, 12 blocks, 13 merged.
 """
 import ctypes as C
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 import torch
@@ -50,9 +53,9 @@ def main():
         lib.mfb200_sparse_decode_attention(C.byref(p), sp)
     torch.cuda.synchronize()
     n = 4096
-    buf = np.zeros((2, n, 16), dtype=np.uint64)
+    buf = np.zeros((2, n, 32), dtype=np.uint64)
     slots = raw.mfb200_debug_trace(buf.ctypes.data, n)
-    assert slots == 16
+    assert slots == 32
     names = ["entry", "idx+bars", "pdl wait", "q staged", "K first", "K last", "V first", "V last", "joined", "published", "exit"]
     t_first = None
     for half in range(2):

@@ -11,7 +11,7 @@ constexpr int kIters = 2000;
 
 // G = 4: HMMA block-diagonal path; G = 1: FHFMA path (decode_pair + 2 predicated FMAs)
 template <int G, int DENS_PCT>
-__global__ void __launch_bounds__(256, 2) loop_kernel(float* out, int iters) {
+__global__ void __launch_bounds__(256, 3) loop_kernel(float* out, int iters) {
     extern __shared__ __align__(128) uint8_t smem[];
     // layout: [8 warps][32 bitmaps 8 B] | [8 warps][64 recs 8 B] | operand blocks 2 KB | nz 8 warps x 4 KB
     uint64_t* bmp = reinterpret_cast<uint64_t*>(smem);
@@ -62,12 +62,12 @@ __global__ void __launch_bounds__(256, 2) loop_kernel(float* out, int iters) {
 }
 
 template <int G, int D>
-void run(const char* name) {
+void run(const char* name, int ctas_per_sm = 2) {
     int sms, clk;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     float* out;
-    const int threads = 256, blocks = sms * 2;
+    const int threads = 256, blocks = sms * ctas_per_sm;
     const int smem = 2048 + 4096 + 2048 + 8 * 4096;
     cudaMalloc(&out, sizeof(float) * threads * blocks);
     cudaFuncSetAttribute(loop_kernel<G, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -82,9 +82,9 @@ void run(const char* name) {
     cudaEventSynchronize(e1);
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
-    const double tiles_per_sm = 2.0 * 8 * 32 * kIters;
-    printf("%-34s %8.3f ms  %5.2f clk per tile per SM (16 tile warps/SM) [%s]\n", name, ms, ms * 1e-3 * clk * 1e3 / tiles_per_sm,
-           cudaGetErrorString(cudaGetLastError()));
+    const double tiles_per_sm = 1.0 * ctas_per_sm * 8 * 32 * kIters;
+    printf("%-34s %8.3f ms  %5.2f clk per tile per SM (%d tile warps/SM) [%s]\n", name, ms, ms * 1e-3 * clk * 1e3 / tiles_per_sm,
+           8 * ctas_per_sm, cudaGetErrorString(cudaGetLastError()));
     cudaFree(out);
 }
 
@@ -93,5 +93,9 @@ int main() {
     run<4, 50>("G=4 HMMA block-diag, 50 % dense");
     run<1, 30>("G=1 FHFMA, 30 % dense");
     run<1, 50>("G=1 FHFMA, 50 % dense");
+    for (int c = 1; c <= 4; ++c) {
+        run<4, 50>("G=4 HMMA block-diag, 50 % dense", c);
+        run<1, 50>("G=1 FHFMA, 50 % dense", c);
+    }
     return 0;
 }
