@@ -11,8 +11,8 @@ path needs NO collective:
     either with ONE all-gather (`gather_heads`: NCCL over NVLink on GPUs, gloo in the CPU tests) or, on the GPUs of one
     node, with NO collective at all (`PeerOutput`): the fused attention launch's split-merge epilogue stores every output
     row straight into all ranks' gathered buffers (peer-to-peer stores over NVLink / NVSwitch) and raises per-unit arrival
-    flags; the consumer side is one tiny wait launch.  A batch-1 layer at 8 ranks: 105 us with the NCCL all-gather,
-    see profiles/ for the peer-store number.
+    flags; the consumer side is one tiny wait launch.  A batch-1 layer at 8 ranks: 105.6 us per layer-step with the NCCL
+    all-gather, 18.9 us with the peer stores (11.5 us for the attention launch alone; profiles/r2_bench_n8.json).
 """
 from __future__ import annotations
 
