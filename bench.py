@@ -482,7 +482,21 @@ def run_extras(args, world, rank, dev, timed, layer_params, launch_all, K):
             torch.cuda.synchronize()
             iso = sorted(a.elapsed_time(b) * 1e3 for a, b in ev)
             iso = iso[len(iso) // 2]
+            # whole decode steps (fused append + attention of all 32 layers, the window growing): one FFI call per step vs
+            # ONE CUDA-graph launch per step with the window lengths in device memory (attention.DecodeStepGraph)
+            from mustafar_b200.attention import DecodeStepGraph, decode_step_layers
+            qb = torch.randn(32, 1, 32, HEAD_DIM, device=dev, dtype=torch.float16)
+            kb = torch.randn(32, 1, 32, HEAD_DIM, device=dev, dtype=torch.float16)
+            ob = torch.empty_like(qb)
+            n_steps = 40
+            decode_step_layers(cs, qb, kb, kb, ob)
+            ms_ffi = timed(lambda i: decode_step_layers(cs, qb, kb, kb, ob), n_steps, sample_clocks=False)
+            graph = DecodeStepGraph(cs, qb, kb, kb, ob)
+            graph.step()
+            ms_graph = timed(lambda i: graph.step(), n_steps, sample_clocks=False)
             return {"workload": "configs[0]/[1] layer: batch 1 x 32 heads x 4K, s=0.5, 32 distinct layer caches (1.4 GB)",
+                    "us_per_layer_step_one_ffi_call_per_step": ms_ffi * 1e3 / (n_steps * 32),
+                    "us_per_layer_step_one_cuda_graph_per_step": ms_graph * 1e3 / (n_steps * 32),
                     "us_per_launch_in_pdl_chain": chain, "us_per_launch_isolated_cold": iso,
                     "frac_of_measured_hbm_in_chain": nbytes / (chain * 1e-6) / 1e9 / peak,
                     "frac_of_measured_hbm_isolated": nbytes / (iso * 1e-6) / 1e9 / peak, "algorithmic_bytes_per_launch": nbytes}

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MFB200_ABI_VERSION 3
+#define MFB200_ABI_VERSION 4
 
 #define MFB200_OK 0
 #define MFB200_EINVAL (-1)  /* bad argument (shape, alignment, null pointer) */
@@ -204,6 +204,11 @@ typedef struct mfb200_decode_params {
     void* workspace;
     /* optional (host pointer, read at launch): also store the output rows into the peers' gathered buffers; NULL = off */
     const mfb200_peer_out* peer;
+    /* optional (DEVICE pointer): the window length is read from *win_len_dev by the kernel instead of from win_len, which
+     * then only gives the CAPACITY the launch is planned for (win_len_dev[0] <= win_len).  Makes a decode step a static
+     * sequence of launches - the same parameter blocks every step - that can be captured ONCE in a CUDA graph and replayed
+     * until the next compression event: see mfb200_decode_layers_static / mfb200_lengths_add.  NULL = off. */
+    const int32_t* win_len_dev;
 } mfb200_decode_params;
 
 /* Round q·k to fp16 and divide by score_div in fp16 like the reference glue does
@@ -254,6 +259,14 @@ int mfb200_decode_step(mfb200_decode_params* p, const void* q, const void* k_new
 int mfb200_decode_step_layers(mfb200_decode_params* const* layers, int n_layers, const void* q, const void* k_new,
                               const void* v_new, void* out, int64_t q_layer_stride, int64_t kv_layer_stride,
                               int64_t out_layer_stride, mfb200_stream_t stream);
+/* Graph-capturable decode step: launches every layer with its parameter block AS IT IS (q / out / k_new / v_new preset,
+ * win_len_dev set, win_len = the window capacity) - nothing on the host changes from step to step, so the sequence
+ *     mfb200_lengths_add(lengths, n_layers, 1) ; mfb200_decode_layers_static(layers, n_layers)
+ * can be captured once and replayed for every decode step between two compression events (llama_mustafar_kernel.py:324:
+ * every 256 tokens the caller compresses, resets the device lengths and captures again). */
+int mfb200_decode_layers_static(const mfb200_decode_params* const* layers, int n_layers, mfb200_stream_t stream);
+/* lengths[i] += delta for i < n (device int32 array; one tiny launch). */
+int mfb200_lengths_add(int32_t* lengths, int n, int delta, mfb200_stream_t stream);
 /* Workspace size that is sufficient for every (comp_len <= max_comp_len, win_len <= max_win_len), plan_hint 0. */
 size_t mfb200_decode_workspace_max(int batch, int kv_heads, int groups, int max_comp_len, int max_win_len,
                                    int sm_count);

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MFB200_LIB", os.path.join(_HERE, "libmustafar_b200.so"))  # override: A/B builds only
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 LAYOUT_KEY = 0
 LAYOUT_VALUE = 1
 F_REF_SCORE_ROUNDING = 1
@@ -39,6 +39,7 @@ class DecodeParams(C.Structure):
         ("mask", _vp), ("mask_stride", _i64),
         ("workspace", _vp),
         ("peer", _vp),
+        ("win_len_dev", _vp),
     ]
 
 
@@ -75,6 +76,8 @@ SIGNATURES = {
     "mfb200_sparse_decode_attention": (_i32, [C.POINTER(DecodeParams), _vp]),
     "mfb200_decode_step": (_i32, [C.POINTER(DecodeParams), _vp, _vp, _vp, _vp, _i32, _vp]),
     "mfb200_decode_step_layers": (_i32, [C.POINTER(C.POINTER(DecodeParams)), _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "mfb200_decode_layers_static": (_i32, [C.POINTER(C.POINTER(DecodeParams)), _i32, _vp]),
+    "mfb200_lengths_add": (_i32, [_vp, _i32, _i32, _vp]),
     "mfb200_decode_workspace_max": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "mfb200_window_append": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
     "mfb200_peer_wait": (_i32, [_vp, _i32, C.c_uint32, _vp, _vp]),

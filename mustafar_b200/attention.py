@@ -554,3 +554,85 @@ def decode_step_layers(caches, q: torch.Tensor, k_new: torch.Tensor, v_new: torc
         c.win_len += 1
         c.maybe_compress()
     return out
+
+
+class DecodeStepGraph:
+    """A decoder's attention path of one decode step as ONE CUDA-graph launch (`mfb200_decode_layers_static`).
+
+    The window length of every layer lives in device memory (`mfb200_decode_params::win_len_dev`), so the launches of a step
+    are identical from step to step: `lengths += 1` followed by one fused (append + attention) launch per layer, captured
+    once and replayed.  The launch is planned for the window's CAPACITY; window chunks that are still empty exit at once.
+    Every 256 tokens the reference schedule compresses the window (llama_mustafar_kernel.py:324): that step runs the
+    compression launches eagerly, rewrites the device lengths and captures the graph again (the compressed length, and with
+    it the work decomposition, has changed).
+
+    q [layers, B, Hq, 128], k_new / v_new [layers, B, Hkv, 128], out [layers, B, Hq, 128] are STATIC fp16 buffers: the caller
+    writes the step's inputs into them before `step()` and reads `out` after it (stream order).  Unmasked decode only.
+    """
+
+    def __init__(self, caches, q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor, out: torch.Tensor):
+        self.caches, self.q, self.k_new, self.v_new, self.out = list(caches), q, k_new, v_new, out
+        c0 = self.caches[0]
+        n = len(self.caches)
+        if not (q.is_cuda and q.dtype == k_new.dtype == v_new.dtype == out.dtype == torch.float16
+                and q.is_contiguous() and k_new.is_contiguous() and v_new.is_contiguous() and out.is_contiguous()):
+            raise RuntimeError("DecodeStepGraph: contiguous float16 CUDA buffers expected (no CPU fallback)")
+        if (q.shape[0] != n or q[0].numel() != c0.units * c0.groups * HEAD_DIM or k_new[0].numel() != c0.units * HEAD_DIM
+                or v_new.shape != k_new.shape or out.shape != q.shape):
+            raise ValueError("DecodeStepGraph: q/out [layers,B,Hq,128], k_new/v_new [layers,B,Hkv,128] expected")
+        self.device = c0.device
+        with torch.cuda.device(self.device):
+            self.lengths = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        self._lib = _lib.load()
+        self._blocks = [_lib.DecodeParams() for _ in range(n)]  # own parameter blocks: the caches' blocks stay host-stepped
+        self._arr = (C.POINTER(_lib.DecodeParams) * n)(*[C.pointer(b) for b in self._blocks])
+        self._graph = None
+        self._captured_comp = None
+        self.captures = 0
+
+    def _capture(self):
+        n = len(self.caches)
+        for l, (c, b) in enumerate(zip(self.caches, self._blocks)):
+            C.memmove(C.byref(b), C.byref(c.make_params(self.q[l], self.out[l], None, self.k_new[l], self.v_new[l])), C.sizeof(b))
+            b.win_len = c.residual_length + COMPRESS_CHUNK  # planned for the most rows the window ever holds
+            b.n_split = 0
+            b.win_len_dev = self.lengths[l:].data_ptr()
+            # inside the graph a layer's predecessor never rewrites this layer's compressed streams: early KV prefetch is safe
+            b.flags = (_lib.F_REF_SCORE_ROUNDING if c.ref_score_rounding else 0) | ((_lib.F_PDL | _lib.F_PDL_EARLY_KV) if c.pdl else 0)
+        self.lengths.copy_(torch.tensor([c.win_len for c in self.caches], dtype=torch.int32), non_blocking=False)
+        sp = torch.cuda.current_stream(self.device).cuda_stream
+        # one eager launch of every kernel the graph contains before capturing (lazy module loading, kernel attributes):
+        # lengths += 0, and the layers without the fused append (side-effect free: `out` is overwritten by the real step)
+        _lib.check(self._lib.mfb200_lengths_add(self.lengths.data_ptr(), n, 0, sp), "mfb200_lengths_add")
+        for b in self._blocks:
+            b.k_new, b.v_new = None, None
+        _lib.check(self._lib.mfb200_decode_layers_static(self._arr, n, sp), "mfb200_decode_layers_static")
+        for l, b in enumerate(self._blocks):
+            b.k_new, b.v_new = self.k_new[l].data_ptr(), self.v_new[l].data_ptr()
+        torch.cuda.current_stream(self.device).synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            cs = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self._lib.mfb200_lengths_add(self.lengths.data_ptr(), n, 1, cs), "mfb200_lengths_add")
+            _lib.check(self._lib.mfb200_decode_layers_static(self._arr, n, cs), "mfb200_decode_layers_static")
+        self._graph = g
+        self._captured_comp = tuple(c.comp_len for c in self.caches)
+        self.captures += 1
+
+    def step(self) -> torch.Tensor:
+        """One decode step for all layers: replays the graph; returns `out` (valid in stream order)."""
+        for c in self.caches:
+            if c.win_len + 1 > c.residual_length + COMPRESS_CHUNK:
+                raise ValueError("DecodeStepGraph: window capacity exceeded")
+        if self._graph is None or self._captured_comp != tuple(c.comp_len for c in self.caches):
+            with torch.cuda.device(self.device):
+                self._capture()
+        self._graph.replay()
+        compressed = False
+        for c in self.caches:
+            c.win_len += 1
+            c._p_stale = True
+            compressed = c.maybe_compress() or compressed
+        if compressed:
+            self._graph = None  # lengths and comp_len changed: the next step captures again
+        return self.out

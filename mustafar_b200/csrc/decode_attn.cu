@@ -223,6 +223,11 @@ __device__ __forceinline__ float ref_round_score(float dot, float div, bool ref_
     return dot / div;
 }
 
+__device__ __forceinline__ uint32_t ld_relaxed_u32_fwd(const void* p) {
+    uint32_t r;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
 // Flat mode: the compressed CTAs partition the launch's units*nblk blocks (unit-major global block index, < 2^31)
 // evenly; a CTA that crosses a unit boundary contributes one segment (= one partial) to each side.
 __host__ __device__ inline uint32_t flat_start(const DecodeArgs& a, uint32_t c) {  // first global block of CTA c
@@ -238,6 +243,13 @@ __host__ __device__ inline int unit_csplits(const DecodeArgs& a, int unit) {
     const uint32_t nblk = a.p.comp_len / kBlockTokens;
     return static_cast<int>(flat_owner(a, (unit + 1) * nblk - 1) - flat_owner(a, unit * nblk)) + 1;
 }
+
+// Window length of this launch: from device memory when the caller runs static (graph-replayed) steps, else the host's value.
+// Only to be called after the PDL wait (the counter is advanced by a launch earlier in the stream).
+__device__ __forceinline__ int cur_win_len(const DecodeArgs& a) {
+    return a.p.win_len_dev != nullptr ? static_cast<int>(ld_relaxed_u32_fwd(a.p.win_len_dev)) : a.p.win_len;
+}
+__device__ __forceinline__ int live_wchunks(const DecodeArgs& a) { return (cur_win_len(a) + kWinTokensPerSplit - 1) / kWinTokensPerSplit; }
 
 // ---- split merge ---------------------------------------------------------------------------------------------
 // Every contributor of a unit writes its fp32 partial (o[G][128], m, l) into its slot as 8-byte entries
@@ -373,6 +385,8 @@ template <int G, bool FLAGGED>
 __device__ __forceinline__ void publish_or_merge(const DecodeArgs& a, int unit, int split, int n_split, uint32_t tag,
                                                  const float* ored, const float* m, const float* l, float* scratch) {
     const int tid = threadIdx.x;
+    // callers count the window chunks the launch was PLANNED for; with a device-side window length fewer may be live
+    if (a.p.win_len_dev != nullptr) n_split += live_wchunks(a) - a.n_wsplit;
     if (FLAGGED && split == n_split - 1) {
         if (tid == 0) {
             MFB_TRACE_AT(9);
@@ -1305,7 +1319,6 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
     const uint32_t lane = lane_id();
     const bool active = warp < kWinWarps;
     const int t0 = wchunk * kWinTokensPerSplit;
-    const int nt = min(kWinTokensPerSplit, p.win_len - t0);
     const int b = unit / p.kv_heads;
     const bool ref_round = (p.flags & MFB200_F_REF_SCORE_ROUNDING) != 0;
 
@@ -1320,6 +1333,9 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
 
     pdl_launch_dependents();
     pdl_wait_prior_grids();  // the window is written by the previous step's launch
+    const int win_len = cur_win_len(a);
+    if (t0 >= win_len) return;  // static steps: the launch is planned for the window's capacity, this chunk is still empty
+    const int nt = min(kWinTokensPerSplit, win_len - t0);
     if (tid == 0) {
         reinterpret_cast<uint32_t*>(ml)[16] = ld_relaxed_u32(epoch_ptr(p, unit)) + 1u;  // this launch's partial tag
         mbar_init(bar, 1);
@@ -1339,15 +1355,15 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
     mbar_wait(bar, 0);
     // fused append: the step's new K/V row belongs at window row win_len-1; the split that owns that row
     // takes it from k_new/v_new (the bulk copy fetched a stale row there) and stores it to the window.
-    if (p.k_new != nullptr && p.win_len - 1 >= t0 && p.win_len - 1 < t0 + nt) {
+    if (p.k_new != nullptr && win_len - 1 >= t0 && win_len - 1 < t0 + nt) {
         if (tid < 32) {
-            const int r = p.win_len - 1 - t0;
+            const int r = win_len - 1 - t0;
             const bool is_v = tid >= 16;
             const int j = tid & 15;
             const uint4 row = reinterpret_cast<const uint4*>(is_v ? p.v_new : p.k_new)[static_cast<int64_t>(unit) * 16 + j];
             reinterpret_cast<uint4*>(smem + (is_v ? sm.vw : sm.kw))[r * 16 + j] = row;
             uint4* gw = reinterpret_cast<uint4*>(static_cast<__half*>(is_v ? p.v_win : p.k_win) +
-                                                 static_cast<int64_t>(unit) * p.win_stride + static_cast<int64_t>(p.win_len - 1) * kHeadDim);
+                                                 static_cast<int64_t>(unit) * p.win_stride + static_cast<int64_t>(win_len - 1) * kHeadDim);
             gw[j] = row;
         }
         __syncthreads();
@@ -1911,6 +1927,30 @@ extern "C" int mfb200_decode_step_layers(mfb200_decode_params* const* layers, in
                                           static_cast<const __half*>(v_new) + l * kv_layer_stride,
                                           static_cast<__half*>(out) + l * out_layer_stride, 0, stream);
         if (rc < 0) return rc;  // layers [0, l) were launched and advanced, layers [l, n) are untouched
+    }
+    return n_layers;
+}
+
+namespace mfb {
+__global__ void lengths_add_kernel(int32_t* lengths, int n, int delta) {
+    pdl_launch_dependents();
+    pdl_wait_prior_grids();  // the previous step's launches still read the old values
+    for (int i = threadIdx.x; i < n; i += blockDim.x) lengths[i] += delta;
+}
+}  // namespace mfb
+
+extern "C" int mfb200_lengths_add(int32_t* lengths, int n, int delta, mfb200_stream_t stream) {
+    MFB_REQUIRE(lengths != nullptr && n > 0, "lengths_add: null pointer / empty range");
+    mfb::lengths_add_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(lengths, n, delta);
+    return launch_status("lengths_add_kernel");
+}
+
+extern "C" int mfb200_decode_layers_static(const mfb200_decode_params* const* layers, int n_layers, mfb200_stream_t stream) {
+    MFB_REQUIRE(layers != nullptr && n_layers >= 0, "decode_layers_static: null pointer");
+    for (int l = 0; l < n_layers; ++l) {
+        MFB_REQUIRE(layers[l] != nullptr && layers[l]->win_len_dev != nullptr, "decode_layers_static: layer %d has no device-side window length", l);
+        const int rc = mfb200_sparse_decode_attention(layers[l], stream);
+        if (rc < 0) return rc;
     }
     return n_layers;
 }

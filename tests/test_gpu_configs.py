@@ -223,3 +223,40 @@ def test_head_sharded_peer_output_equals_all_gather(world, hkv, groups):
     assert not any(po.timed_out() for po in peers)
     for po in peers:
         po.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,hkv,groups,sparsity", [(1, 8, 1, 0.5), (2, 2, 4, 0.7)])
+def test_decode_step_graph_equals_eager_steps(b, hkv, groups, sparsity):
+    """A decode step as ONE CUDA-graph launch with the window length in device memory (attention.DecodeStepGraph) against the
+    eager per-layer steps: bit-identical outputs and cache contents over 300 steps - through every window-chunk count
+    (the graph is planned for the window's capacity) and a compression event (the graph is captured again)."""
+    from mustafar_b200.attention import DecodeStepGraph, MustafarKVCache
+    layers, T0, steps = 3, 330, 300
+    gen = torch.Generator().manual_seed(11)
+    caches_a, caches_b = [], []
+    for _ in range(layers):
+        k = torch.randn(b, hkv, T0, 128, generator=gen).half().cuda()
+        v = torch.randn(b, hkv, T0, 128, generator=gen).half().cuda()
+        for lst in (caches_a, caches_b):
+            c = MustafarKVCache(b, hkv, groups, T0 + steps + 64, sparsity, sparsity)
+            c.prefill(k, v)
+            lst.append(c)
+    q = torch.zeros(layers, b, hkv * groups, 128, dtype=torch.float16, device="cuda")
+    kn = torch.zeros(layers, b, hkv, 128, dtype=torch.float16, device="cuda")
+    vn = torch.zeros_like(kn)
+    out = torch.zeros_like(q)
+    graph = DecodeStepGraph(caches_b, q, kn, vn, out)
+    for t in range(steps):
+        q.copy_(torch.randn(q.shape, generator=gen).half())
+        kn.copy_(torch.randn(kn.shape, generator=gen).half())
+        vn.copy_(torch.randn(vn.shape, generator=gen).half())
+        want = torch.stack([c.decode_step(q[l].view(b, -1, 1, 128), kn[l].view(b, hkv, 1, 128), vn[l].view(b, hkv, 1, 128)).view(b, -1, 128)
+                            for l, c in enumerate(caches_a)])
+        got = graph.step()
+        assert torch.equal(got, want), (t, (got.float() - want.float()).abs().max().item())
+    assert graph.captures == 2  # one compression event inside the run (window 42 -> 288 at step 246)
+    for ca, cb in zip(caches_a, caches_b):
+        assert ca.comp_len == cb.comp_len == 512 and ca.win_len == cb.win_len
+        assert torch.equal(ca.k_win[:, : ca.win_len], cb.k_win[:, : cb.win_len])
+        assert torch.equal(ca.k.idx, cb.k.idx) and torch.equal(ca.v.bmp, cb.v.bmp)
