@@ -226,13 +226,15 @@ def test_head_sharded_peer_output_equals_all_gather(world, hkv, groups):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("b,hkv,groups,sparsity", [(1, 8, 1, 0.5), (2, 2, 4, 0.7)])
-def test_decode_step_graph_equals_eager_steps(b, hkv, groups, sparsity):
+@pytest.mark.parametrize("b,hkv,groups,sparsity,T0,steps,layers,captures,comp_end", [
+    (1, 8, 1, 0.5, 330, 300, 3, 2, 512), (2, 2, 4, 0.7, 330, 300, 3, 2, 512),
+    (16, 8, 4, 0.7, 8192 - 20, 60, 2, 2, 8192),  # BASELINE config 3's geometry: the flat plan, compression at step 52
+])
+def test_decode_step_graph_equals_eager_steps(b, hkv, groups, sparsity, T0, steps, layers, captures, comp_end):
     """A decode step as ONE CUDA-graph launch with the window length in device memory (attention.DecodeStepGraph) against the
     eager per-layer steps: bit-identical outputs and cache contents over 300 steps - through every window-chunk count
     (the graph is planned for the window's capacity) and a compression event (the graph is captured again)."""
     from mustafar_b200.attention import DecodeStepGraph, MustafarKVCache
-    layers, T0, steps = 3, 330, 300
     gen = torch.Generator().manual_seed(11)
     caches_a, caches_b = [], []
     for _ in range(layers):
@@ -255,8 +257,8 @@ def test_decode_step_graph_equals_eager_steps(b, hkv, groups, sparsity):
                             for l, c in enumerate(caches_a)])
         got = graph.step()
         assert torch.equal(got, want), (t, (got.float() - want.float()).abs().max().item())
-    assert graph.captures == 2  # one compression event inside the run (window 42 -> 288 at step 246)
+    assert graph.captures == captures  # one compression event inside the run (small cases: window 42 -> 288 at step 246)
     for ca, cb in zip(caches_a, caches_b):
-        assert ca.comp_len == cb.comp_len == 512 and ca.win_len == cb.win_len
+        assert ca.comp_len == cb.comp_len == comp_end and ca.win_len == cb.win_len
         assert torch.equal(ca.k_win[:, : ca.win_len], cb.k_win[:, : cb.win_len])
         assert torch.equal(ca.k.idx, cb.k.idx) and torch.equal(ca.v.bmp, cb.v.bmp)
