@@ -627,6 +627,7 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
             for (int w = 0; w < kTileWarps; ++w) {
                 if constexpr (G >= 4) {
 #pragma unroll
+#if MFB_SCORE_PITCH % 4 == 0
                     for (int i = 0; i < TPL; i += 4) {
                         const float4 t = *reinterpret_cast<const float4*>(sp + w * G * SPP + tok(i));
                         sc[i] += t.x;
@@ -634,6 +635,13 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
                         sc[i + 2] += t.z;
                         sc[i + 3] += t.w;
                     }
+#else
+                    for (int i = 0; i < TPL; i += 2) {
+                        const float2 t = *reinterpret_cast<const float2*>(sp + w * G * SPP + tok(i));
+                        sc[i] += t.x;
+                        sc[i + 1] += t.y;
+                    }
+#endif
                 } else {
 #pragma unroll
                     for (int i = 0; i < TPL; i += 2) {

@@ -30,7 +30,12 @@
 
 namespace mfb {
 
-constexpr int kTcRowPitch = 72;  // floats per [g] row of the partial-score buffers of the G >= 4 variants (64 + 8)
+#ifndef MFB_SCORE_PITCH
+#define MFB_SCORE_PITCH 74
+#endif
+constexpr int kTcRowPitch = MFB_SCORE_PITCH;  // floats per [g] row of the partial-score buffers of the G >= 4 variants: 64 + 10 keeps the K warps'
+                                              // fragment stores (rows g0 / g0+2 within a half-warp) and the softmax warp's 8-byte reads
+                                              // (two heads per half-warp) free of bank conflicts (72: 2-way conflicts on the stores; -1 %)
 // Operand blocks: the B fragments of one 4-tile group sit in ONE aligned block, row g = operand[g][4 tiles] (8 bytes), row G
 // = zeros (what the lanes that are not live in an MMA read).  An LDS.64 whose 5..9 distinct addresses share a 128-byte
 // line costs one wavefront; the same rows 144 bytes apart cost 2.4 (tools/ubench.cu, profiles/r2_ubench_lds.txt).
