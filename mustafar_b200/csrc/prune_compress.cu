@@ -15,6 +15,10 @@
 // leave as one contiguous (<=128 B) store per tile.
 #include "common.cuh"
 
+#ifndef MFB_SELECT_EARLY_EXIT
+#define MFB_SELECT_EARLY_EXIT 1
+#endif
+
 namespace mfb {
 
 constexpr int kPitch = kHeadDim + 2;  // halves; 65 words -> conflict-free column reads
@@ -34,12 +38,28 @@ __device__ __forceinline__ uint32_t warp_kth_smallest(uint32_t kx, uint32_t ky, 
     // round's u up by 2^(bit-1), rejecting it moves it down by 2^(bit-1) (fields never carry or borrow).
     uint32_t u = 0x80008000u + ((1u << 14) - 1u) * kRep;
     const uint32_t k255 = static_cast<uint32_t>(k) * 255u;
+#if MFB_SELECT_EARLY_EXIT
+    const uint32_t km1_255 = k255 - 255u;
+#endif
     bool accept = false;
 #pragma unroll
     for (int bit = 14; bit >= 0; --bit) {
         uint32_t flags;
         asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(flags) : "r"(u - kx), "r"(u - ky));  // sign bytes of the 4 fields
         const uint32_t c255 = __reduce_add_sync(0xffffffffu, __dp4a(flags, 0x01010101u, 0u));
+#if MFB_SELECT_EARLY_EXIT
+        // Exactly k-1 keys lie below cand: the k-th smallest is the smallest key >= cand - one warp minimum instead of the
+        // remaining rounds.  A bisection over VALUES keeps halving an interval that soon holds a single key: on Gaussian rows
+        // this exit is taken after 10.3 rounds on average instead of 15 (warp-uniform branch).
+        if (c255 == km1_255) {
+            uint32_t m01, m23;  // 0xffff in the fields whose key is below cand (flag bytes 0xFF), else 0
+            asm("prmt.b32 %0, %1, %1, 0x1100;" : "=r"(m01) : "r"(flags));
+            asm("prmt.b32 %0, %1, %1, 0x3322;" : "=r"(m23) : "r"(flags));
+            const uint32_t cx = kx | m01, cy = ky | m23;  // keys below cand become 0xffff (keys are <= 0x7fff)
+            const uint32_t a = min(cx & 0xffffu, cx >> 16), b = min(cy & 0xffffu, cy >> 16);
+            return __reduce_min_sync(0xffffffffu, min(a, b));
+        }
+#endif
         accept = c255 < k255;  // fewer than k keys below cand: the k-th smallest is >= cand
         if (bit > 0) {
             const uint32_t delta = (1u << (bit - 1)) * kRep;
