@@ -6,7 +6,7 @@ set -x
 export MFB200_BENCH_NO_MODEL=1
 # 1. launch list of a short bench run (per-launch durations: cold-cache and serialised under ncu; shares matter)
 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${TAG}_bench_plain.log 2>&1 || exit 1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:compress|sparse_decode|window_append|prune|formulation|peer_wait|lengths_add" -c 1500 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${TAG}_ncu_bench.log 2>&1
 # 2. --set full captures of the decode kernel at the BASELINE shapes
 for c in cfg5 cfg3 cfg1 mid1 cfg4s; do
