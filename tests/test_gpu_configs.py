@@ -5,6 +5,8 @@ numpy oracle in tests/test_torch_oracle.py) and, for the compression format, the
 (kernel/compression.py) cross-compiled from /root/reference into oracle/_ref/triton/*.cubin and launched here.
 Tolerances: bit-exact for bitmaps / offsets / packed values; 2e-3 max-abs, 1e-3 mean-abs (north_star) for attention.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -262,3 +264,17 @@ def test_decode_step_graph_equals_eager_steps(b, hkv, groups, sparsity, T0, step
         assert ca.comp_len == cb.comp_len == comp_end and ca.win_len == cb.win_len
         assert torch.equal(ca.k_win[:, : ca.win_len], cb.k_win[:, : cb.win_len])
         assert torch.equal(ca.k.idx, cb.k.idx) and torch.equal(ca.v.bmp, cb.v.bmp)
+
+
+@pytest.mark.gpu
+def test_head_sharded_peer_output_across_processes():
+    """The real thing: one process per GPU, cudaIpc-mapped gathered buffers, NCCL all-gather as the reference
+    (tools/peer_check.py under torchrun).  Needs two GPUs on the box; skipped otherwise."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29577", os.path.join(root, "tools", "peer_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "bit-equal to the all-gather on every rank: True" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
