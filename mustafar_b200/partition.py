@@ -176,7 +176,14 @@ class PeerOutput:
         """Host-syncing: did any wait give up (a peer died)?"""
         return bool(self._mem[self.nbytes - 256: self.nbytes - 252].view(torch.int32).item())
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown: the driver releases the memory with the context
+            pass
+
     def close(self) -> None:
+        """Unmap the peers' blocks and free the own one (after every rank is done with it: synchronise / barrier first)."""
         for q in self._opened:
             self._L.mfb200_ipc_close(q)
         self._opened = []
