@@ -15,6 +15,9 @@
 // leave as one contiguous (<=128 B) store per tile.
 #include "common.cuh"
 
+#ifndef MFB_LOOKBACK_SLEEP
+#define MFB_LOOKBACK_SLEEP 40
+#endif
 #ifndef MFB_SELECT_EARLY_EXIT
 #define MFB_SELECT_EARLY_EXIT 1
 #endif
@@ -431,7 +434,7 @@ __device__ __forceinline__ int32_t lookback_exclusive(unsigned long long* st, in
         while (true) {  // block -1 is a virtual predecessor whose inclusive prefix is the unit's carry-in
             s = j >= 0 ? ld_relaxed_u64(&st[j]) : (kStPrefix | static_cast<uint32_t>(j == -1 ? carry : 0));
             if (!__any_sync(0xffffffffu, (s >> 32) == 0)) break;
-            __nanosleep(40);
+            __nanosleep(MFB_LOOKBACK_SLEEP);
         }
         const int32_t val = static_cast<int32_t>(static_cast<uint32_t>(s));
         const uint32_t pm = __ballot_sync(0xffffffffu, (s >> 32) == 2);
@@ -452,7 +455,11 @@ __device__ __forceinline__ void prefill_block_body(const PrefillArgs& a, int whi
     __shared__ int32_t warp_tot[8];
     __shared__ int32_t s_excl;
     __shared__ int s_tb;
-    const int64_t u = blockIdx.y, units = gridDim.y, nblk = gridDim.x;
+    // Units vary fastest in dispatch order: the predecessor of a block in its unit's look-back chain (same unit, previous
+    // ticket) was dispatched `units` CTAs earlier and has normally published its inclusive prefix by the time this CTA asks
+    // for it.  (Blocks of one unit dispatched back to back all reached the look-back together: warp 0 of every CTA spun on
+    // its neighbours - 29 % of the kernel's executed instructions were that loop.)
+    const int64_t u = blockIdx.x, units = gridDim.x, nblk = gridDim.y;
     if (threadIdx.x == 0) s_tb = static_cast<int>(atomicAdd(&a.ticket[static_cast<int64_t>(which) * units + u], 1u));
     __syncthreads();
     const int tb = s_tb;
@@ -747,7 +754,8 @@ extern "C" int mfb200_compress_prefill(const void* k, const void* v, const int64
     a.overflow = overflow;
     a.status = static_cast<unsigned long long*>(status_ws);
     a.ticket = reinterpret_cast<unsigned int*>(a.status + 2 * units * nblk);
-    dim3 grid(static_cast<unsigned>(nblk), static_cast<unsigned>(units), 2);
+    MFB_REQUIRE(nblk <= 65535, "compress_prefill: more than 65535 blocks per unit");
+    dim3 grid(static_cast<unsigned>(units), static_cast<unsigned>(nblk), 2);
     compress_prefill_kernel<<<grid, kCompressThreads, 0, s>>>(a);
     return launch_status("compress_prefill_kernel");
 }
