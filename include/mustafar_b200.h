@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MFB200_ABI_VERSION 4
+#define MFB200_ABI_VERSION 5
 
 #define MFB200_OK 0
 #define MFB200_EINVAL (-1)  /* bad argument (shape, alignment, null pointer) */
@@ -209,6 +209,14 @@ typedef struct mfb200_decode_params {
      * sequence of launches - the same parameter blocks every step - that can be captured ONCE in a CUDA graph and replayed
      * until the next compression event: see mfb200_decode_layers_static / mfb200_lengths_add.  NULL = off. */
     const int32_t* win_len_dev;
+    /* optional fused rotary position embedding (models/llama_mustafar_kernel.py:238-253: apply_rotary_pos_emb in front of
+     * the attention): fp16 cos / sin rows of 128 entries per SEQUENCE (the layout transformers' rotary_emb returns: entry c
+     * and c+64 hold the same angle), sequence b at rope_cos + b*rope_stride (stride 0 = one row for all).  When set, q and
+     * k_new are taken as UNROTATED: the kernel attends with  x*cos + rotate_half(x)*sin  (each product and the sum rounded
+     * to fp16, exactly the arithmetic of the reference's fp16 tensor ops) and appends the rotated K row.  Both NULL = off. */
+    const void* rope_cos;
+    const void* rope_sin;
+    int64_t rope_stride; /* halves */
 } mfb200_decode_params;
 
 /* Round q·k to fp16 and divide by score_div in fp16 like the reference glue does

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MFB200_LIB", os.path.join(_HERE, "libmustafar_b200.so"))  # override: A/B builds only
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 LAYOUT_KEY = 0
 LAYOUT_VALUE = 1
 F_REF_SCORE_ROUNDING = 1
@@ -40,6 +40,9 @@ class DecodeParams(C.Structure):
         ("workspace", _vp),
         ("peer", _vp),
         ("win_len_dev", _vp),
+        ("rope_cos", _vp),
+        ("rope_sin", _vp),
+        ("rope_stride", C.c_int64),
     ]
 
 

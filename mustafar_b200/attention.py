@@ -364,10 +364,26 @@ class MustafarKVCache:
         p.k_win, p.v_win, p.win_stride = self.k_win.data_ptr(), self.v_win.data_ptr(), self.win_cap * HEAD_DIM
         return p
 
+    def _rope_fields(self, p: _lib.DecodeParams, rope) -> None:
+        """rope = (cos, sin): fp16 rows of 128 entries, one per sequence ([B, 1, 128], what transformers' rotary_emb returns
+        for position_ids [B, 1]) or one for all; None = q / k_new are already rotated."""
+        if rope is None:
+            p.rope_cos, p.rope_sin, p.rope_stride = None, None, 0
+            return
+        cos, sin = rope
+        for t in (cos, sin):
+            if not (t.is_cuda and t.dtype == torch.float16 and t.is_contiguous() and t.shape[-1] == HEAD_DIM
+                    and t.numel() in (HEAD_DIM, self.batch * HEAD_DIM)):
+                raise ValueError("rope: contiguous float16 CUDA cos/sin of shape [B, 1, 128] or [1, 1, 128] expected")
+        if cos.numel() != sin.numel():
+            raise ValueError("rope: cos and sin differ in shape")
+        p.rope_cos, p.rope_sin = cos.data_ptr(), sin.data_ptr()
+        p.rope_stride = HEAD_DIM if cos.numel() == self.batch * HEAD_DIM else 0
+
     def make_params(self, q: torch.Tensor, out: torch.Tensor, mask: Optional[torch.Tensor] = None,
-                    k_new: Optional[torch.Tensor] = None, v_new: Optional[torch.Tensor] = None) -> _lib.DecodeParams:
+                    k_new: Optional[torch.Tensor] = None, v_new: Optional[torch.Tensor] = None, rope=None) -> _lib.DecodeParams:
         """Fills the (cached) C parameter block for one launch at the cache's current lengths.  When k_new/v_new
-        are given, self.win_len must already count the new token."""
+        are given, self.win_len must already count the new token.  rope: see `_rope_fields` (fused rotary embedding)."""
         p = self._params()
         n_split, ws_bytes = self._plan()
         assert ws_bytes <= self._ws_bytes
@@ -383,7 +399,24 @@ class MustafarKVCache:
             p.mask, p.mask_stride = mask.data_ptr(), mask.stride(0)
         else:
             p.mask, p.mask_stride = None, 0
+        self._rope_fields(p, rope)
         return p
+
+    def static_step_params(self, q: torch.Tensor, out: torch.Tensor, k_new: Optional[torch.Tensor], v_new: Optional[torch.Tensor],
+                           win_len_dev: int, rope=None) -> _lib.DecodeParams:
+        """An OWN parameter block (the cache's long-lived block stays host-stepped) for a STATIC decode step: the launch is
+        planned for the most rows the window ever holds and reads the live window length from the int32 at the DEVICE address
+        `win_len_dev`, so the same launch is valid at every step until the next compression - what a CUDA graph needs
+        (include/mustafar_b200.h: mfb200_decode_params::win_len_dev).  Unmasked decode only."""
+        b = _lib.DecodeParams()
+        C.memmove(C.byref(b), C.byref(self.make_params(q, out, None, k_new, v_new, rope)), C.sizeof(b))
+        self._rope_fields(self._p, None)  # the long-lived block is shared with the host-stepped fast path
+        b.win_len = self.residual_length + COMPRESS_CHUNK
+        b.n_split = 0  # planned by the library for that capacity
+        b.win_len_dev = win_len_dev
+        # inside a captured step nothing rewrites this cache's compressed streams: the early KV prefetch is safe
+        b.flags = (_lib.F_REF_SCORE_ROUNDING if self.ref_score_rounding else 0) | ((_lib.F_PDL | _lib.F_PDL_EARLY_KV) if self.pdl else 0)
+        return b
 
     def set_peer_output(self, peer) -> None:
         """Head-sharded decode: `peer` = a `_lib.PeerOut` block (partition.PeerOutput keeps it alive and up to date) whose
@@ -441,11 +474,13 @@ class MustafarKVCache:
             p.flags = self._flags()
         return p
 
-    def decode_step(self, query_states, key_states, value_states, attention_mask=None, out=None):
+    def decode_step(self, query_states, key_states, value_states, attention_mask=None, out=None, rope=None):
         """One reference decode step of the attention block (llama_mustafar_kernel.py:256-398) in ONE launch:
         the new token's K/V rows [B, Hkv, 1, 128] are appended to the window by the attention kernel itself,
         which attends over compressed + window (incl. the new token); then the periodic compression.
-        The unmasked case is a single FFI call (mfb200_decode_step) on the cache's long-lived parameter block."""
+        The unmasked case is a single FFI call (mfb200_decode_step) on the cache's long-lived parameter block.
+        rope = (cos, sin) fuses the rotary embedding of `:238-253` into the launch: query_states / key_states are then the
+        UNROTATED projections (see `_rope_fields`); the window receives the rotated key row."""
         q, k, v = query_states, key_states, value_states
         if not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
             q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
@@ -456,7 +491,7 @@ class MustafarKVCache:
             raise ValueError("decode_step: q [B,Hq,1,128], k/v [B,Hkv,1,128] expected and window capacity not exceeded")
         if out is None:
             out = torch.empty_like(q)
-        if attention_mask is None:
+        if attention_mask is None and rope is None:
             self._sync_step_params()
             with torch.cuda.device(self.device):
                 rc = self._step(self._p_ref, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), self._sm_count,
@@ -468,10 +503,13 @@ class MustafarKVCache:
         else:
             self.win_len += 1
             try:
-                self._launch(self.make_params(q, out, self._mask2d(attention_mask), k, v))
+                self._launch(self.make_params(q, out, self._mask2d(attention_mask), k, v, rope))
             except Exception:
                 self.win_len -= 1
                 raise
+            finally:
+                if self._p is not None:
+                    self._rope_fields(self._p, None)
         self.maybe_compress()
         return out
 
@@ -593,12 +631,8 @@ class DecodeStepGraph:
     def _capture(self):
         n = len(self.caches)
         for l, (c, b) in enumerate(zip(self.caches, self._blocks)):
-            C.memmove(C.byref(b), C.byref(c.make_params(self.q[l], self.out[l], None, self.k_new[l], self.v_new[l])), C.sizeof(b))
-            b.win_len = c.residual_length + COMPRESS_CHUNK  # planned for the most rows the window ever holds
-            b.n_split = 0
-            b.win_len_dev = self.lengths[l:].data_ptr()
-            # inside the graph a layer's predecessor never rewrites this layer's compressed streams: early KV prefetch is safe
-            b.flags = (_lib.F_REF_SCORE_ROUNDING if c.ref_score_rounding else 0) | ((_lib.F_PDL | _lib.F_PDL_EARLY_KV) if c.pdl else 0)
+            C.memmove(C.byref(b), C.byref(c.static_step_params(self.q[l], self.out[l], self.k_new[l], self.v_new[l],
+                                                               self.lengths[l:].data_ptr())), C.sizeof(b))
         self.lengths.copy_(torch.tensor([c.win_len for c in self.caches], dtype=torch.int32), non_blocking=False)
         sp = torch.cuda.current_stream(self.device).cuda_stream
         # one eager launch of every kernel the graph contains before capturing (lazy module loading, kernel attributes):

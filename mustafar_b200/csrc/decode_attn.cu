@@ -249,6 +249,27 @@ __host__ __device__ inline int unit_csplits(const DecodeArgs& a, int unit) {
 __device__ __forceinline__ int cur_win_len(const DecodeArgs& a) {
     return a.p.win_len_dev != nullptr ? static_cast<int>(ld_relaxed_u32_fwd(a.p.win_len_dev)) : a.p.win_len;
 }
+// Optional fused rotary embedding (mfb200_decode_params::rope_cos): element c of a 128-half q / new-K row becomes
+// x[c]*cos[c] + rotate_half(x)[c]*sin[c], rotate_half(x) = (-x[64..127], x[0..63]).  Products and sum are each rounded to fp16
+// (the _rn intrinsics also forbid FMA contraction): bit-identical to transformers' apply_rotary_pos_emb on fp16 tensors, whose
+// elementwise kernels compute in fp32 and round once per op (fp32 holds the product of two halves exactly).
+struct RopeRows {
+    const __half* cs;  // nullptr = off
+    const __half* sn;
+};
+__device__ __forceinline__ RopeRows rope_rows(const mfb200_decode_params& p, int unit) {
+    if (p.rope_cos == nullptr) return RopeRows{nullptr, nullptr};
+    const int64_t off = static_cast<int64_t>(unit / p.kv_heads) * p.rope_stride;
+    return RopeRows{static_cast<const __half*>(p.rope_cos) + off, static_cast<const __half*>(p.rope_sin) + off};
+}
+__device__ __forceinline__ __half rope_value(__half x, __half partner, __half cs, __half sn, bool low_half) {
+    return __hadd_rn(__hmul_rn(x, cs), __hmul_rn(low_half ? __hneg(partner) : partner, sn));
+}
+__device__ __forceinline__ __half rope_elem(const RopeRows& r, const __half* row, int c) {
+    const __half x = row[c];
+    return r.cs == nullptr ? x : rope_value(x, row[c ^ 64], r.cs[c], r.sn[c], c < 64);
+}
+
 __device__ __forceinline__ int live_wchunks(const DecodeArgs& a) { return (cur_win_len(a) + kWinTokensPerSplit - 1) / kWinTokensPerSplit; }
 
 // ---- split merge ---------------------------------------------------------------------------------------------
@@ -569,14 +590,16 @@ __device__ __forceinline__ void compressed_split(const DecodeArgs& a, uint8_t* s
     }
     {
         const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
+        const RopeRows rp = rope_rows(p, unit);
         if constexpr (G >= 4) {
             constexpr int BH = oper_block_bytes(G) / 2;  // halves per operand block
-            for (int i = tid; i < G * kHeadDim; i += blockDim.x) qs[((i & 127) >> 2) * BH + (i >> 7) * 4 + (i & 3)] = q[i];
+            for (int i = tid; i < G * kHeadDim; i += blockDim.x)
+                qs[((i & 127) >> 2) * BH + (i >> 7) * 4 + (i & 3)] = rope_elem(rp, q + (i & ~127), i & 127);
             // the zero rows of the q blocks and of both p buffers (64 + 32 blocks, 8 bytes each)
             for (int i = tid; i < 32 + 2 * 16; i += blockDim.x)
                 *reinterpret_cast<uint2*>((i < 32 ? qs + i * BH : ps + (i - 32) * BH) + G * 4) = make_uint2(0u, 0u);
         } else {
-            for (int i = tid; i < G * kHeadDim; i += blockDim.x) qs[(i & 127) * G + (i >> 7)] = q[i];
+            for (int i = tid; i < G * kHeadDim; i += blockDim.x) qs[(i & 127) * G + (i >> 7)] = rope_elem(rp, q + (i & ~127), i & 127);
         }
     }
     __syncthreads();  // q staged (threads of every warp contribute) before the K warps read it
@@ -1010,9 +1033,10 @@ __device__ __forceinline__ void compressed_split_tc(const DecodeArgs& a, uint8_t
     {   // q as the K-major B operand of the score MMAs: [channel group][row g][8 channels]; rows >= G are zero
         const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
         __half* qb = reinterpret_cast<__half*>(smem + sm.qb);
+        const RopeRows rp = rope_rows(p, unit);
         for (int i = tid; i < kQbBytes / 2; i += blockDim.x) {
             const int kg = i >> 6, row = (i >> 3) & 7, e = i & 7;
-            qb[i] = row < G ? q[row * kHeadDim + kg * 8 + e] : __ushort_as_half(0);
+            qb[i] = row < G ? rope_elem(rp, q + row * kHeadDim, kg * 8 + e) : __ushort_as_half(0);
         }
     }
     fence_async_smem();  // qb / the zeroed p buffers were written through the generic proxy, the MMAs read them through the async one
@@ -1357,7 +1381,9 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
     }
     {
         const __half* q = static_cast<const __half*>(p.q) + static_cast<int64_t>(unit) * G * kHeadDim;
-        for (int i = tid; i < G * kHeadDim; i += blockDim.x) qs[win_q_index(i >> 7, i & 127)] = __half2float(q[i]);
+        const RopeRows rp = rope_rows(p, unit);
+        for (int i = tid; i < G * kHeadDim; i += blockDim.x)
+            qs[win_q_index(i >> 7, i & 127)] = __half2float(rope_elem(rp, q + (i & ~127), i & 127));
     }
     __syncthreads();  // q staged, barrier initialised
     mbar_wait(bar, 0);
@@ -1368,7 +1394,21 @@ __device__ __forceinline__ void window_split(const DecodeArgs& a, uint8_t* smem,
             const int r = win_len - 1 - t0;
             const bool is_v = tid >= 16;
             const int j = tid & 15;
-            const uint4 row = reinterpret_cast<const uint4*>(is_v ? p.v_new : p.k_new)[static_cast<int64_t>(unit) * 16 + j];
+            uint4 row = reinterpret_cast<const uint4*>(is_v ? p.v_new : p.k_new)[static_cast<int64_t>(unit) * 16 + j];
+            if (!is_v && p.rope_cos != nullptr) {  // the cache holds rotated keys (llama_mustafar_kernel.py:253, :270)
+                const RopeRows rp = rope_rows(p, unit);
+                const uint4 other = reinterpret_cast<const uint4*>(p.k_new)[static_cast<int64_t>(unit) * 16 + (j ^ 8)];
+                const uint4 c4 = reinterpret_cast<const uint4*>(rp.cs)[j], s4 = reinterpret_cast<const uint4*>(rp.sn)[j];
+                const __half* x = reinterpret_cast<const __half*>(&row);
+                const __half* y = reinterpret_cast<const __half*>(&other);
+                const __half* cc = reinterpret_cast<const __half*>(&c4);
+                const __half* ss = reinterpret_cast<const __half*>(&s4);
+                uint4 rot;
+                __half* r8 = reinterpret_cast<__half*>(&rot);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r8[e] = rope_value(x[e], y[e], cc[e], ss[e], j < 8);
+                row = rot;
+            }
             reinterpret_cast<uint4*>(smem + (is_v ? sm.vw : sm.kw))[r * 16 + j] = row;
             uint4* gw = reinterpret_cast<uint4*>(static_cast<__half*>(is_v ? p.v_win : p.k_win) +
                                                  static_cast<int64_t>(unit) * p.win_stride + static_cast<int64_t>(win_len - 1) * kHeadDim);
@@ -1831,6 +1871,11 @@ extern "C" int mfb200_sparse_decode_attention(const mfb200_decode_params* p, mfb
                     "decode: window buffers must be 16-byte aligned");
     }
     if (p->mask) MFB_REQUIRE(p->mask_stride >= p->comp_len + p->win_len, "decode: mask_stride too small");
+    MFB_REQUIRE((p->rope_cos == nullptr) == (p->rope_sin == nullptr), "decode: rope_cos and rope_sin go together");
+    if (p->rope_cos)
+        MFB_REQUIRE(((reinterpret_cast<uintptr_t>(p->rope_cos) | reinterpret_cast<uintptr_t>(p->rope_sin)) & 15) == 0 &&
+                        p->rope_stride >= 0 && p->rope_stride % 8 == 0,
+                    "decode: rope_cos/rope_sin must be 16-byte aligned fp16 rows (stride a multiple of 8 halves, 0 = shared)");
     MFB_REQUIRE((p->k_new == nullptr) == (p->v_new == nullptr), "decode: k_new and v_new must be given together");
     if (p->k_new)
         MFB_REQUIRE(p->win_len >= 1 && ((reinterpret_cast<uintptr_t>(p->k_new) | reinterpret_cast<uintptr_t>(p->v_new)) & 15) == 0,

@@ -10,7 +10,7 @@
 // read once with 8-byte coalesced loads (a warp reads one 256-byte token row), optionally pruned in
 // registers by a warp-level radix select on the 15-bit magnitudes, and parked in shared memory with
 // a 65-word row pitch so that both the row-wise (V) and the column-wise (K) tile reads are free of
-// bank conflicts.  Bitmap words come from __ballot_sync + __brev (MSB = element 0), ranks from
+// bank conflicts.  Bitmap words come from __ballot_sync over lanes that hold the elements in reverse order (MSB = element 0), ranks from
 // __popc of the ballot below the lane.  Packed tiles are assembled in a per-warp staging line and
 // leave as one contiguous (<=128 B) store per tile.
 #include "common.cuh"
@@ -112,18 +112,23 @@ __device__ __forceinline__ void load_block(const __half* __restrict__ x, int64_t
     }
 }
 
-// element (tile-local index e in {lane, lane+32}) of tile `tl` (0..127 inside the block)
+// Elements (tile-local indices 31 - lane and 63 - lane) of tile `tl` (0..127 inside the block).  Lanes take the elements in
+// REVERSE order so that a ballot over the lanes IS the bitmap word (bit 31 = element 0 = the format's MSB-first order)
+// without a BREV; the elements before a lane's are then the bits ABOVE its own (lane_above / lane_bit).
 template <int LAYOUT>
 __device__ __forceinline__ void tile_elems(const uint16_t* tile, int tl, uint32_t lane, uint32_t& e0, uint32_t& e1) {
+    const uint32_t el = 31u - lane;
     if (LAYOUT == MFB200_LAYOUT_KEY) {  // tile = channel tl, elements = tokens
-        e0 = tile[lane * kPitch + tl];
-        e1 = tile[(lane + 32) * kPitch + tl];
+        e0 = tile[el * kPitch + tl];
+        e1 = tile[(el + 32) * kPitch + tl];
     } else {  // tile = (half = tl/64, token = tl%64), elements = channels of that half
         const int r = tl & 63, hf = tl >> 6;
-        e0 = tile[r * kPitch + hf * 64 + lane];
-        e1 = tile[r * kPitch + hf * 64 + 32 + lane];
+        e0 = tile[r * kPitch + hf * 64 + el];
+        e1 = tile[r * kPitch + hf * 64 + 32 + el];
     }
 }
+__device__ __forceinline__ uint32_t lane_above(uint32_t lane) { return lane == 31 ? 0u : (0xfffffffeu << lane); }  // bits of the elements before mine
+__device__ __forceinline__ uint32_t lane_bit(uint32_t lane) { return 1u << lane; }
 
 template <int LAYOUT>
 __global__ void __launch_bounds__(kCompressThreads)
@@ -141,8 +146,8 @@ compress_count_kernel(const __half* __restrict__ x, int64_t tokens, int prune_k,
     for (int i = 0; i < 16; ++i) {
         uint32_t e0, e1;
         tile_elems<LAYOUT>(tile, warp * 16 + i, lane, e0, e1);
-        const uint32_t hi = __brev(__ballot_sync(0xffffffffu, (e0 & 0x7fffu) != 0));
-        const uint32_t lo = __brev(__ballot_sync(0xffffffffu, (e1 & 0x7fffu) != 0));
+        const uint32_t hi = __ballot_sync(0xffffffffu, (e0 & 0x7fffu) != 0);
+        const uint32_t lo = __ballot_sync(0xffffffffu, (e1 & 0x7fffu) != 0);
         if (lane == static_cast<uint32_t>(i)) {
             my_hi = hi;
             my_lo = lo;
@@ -211,8 +216,7 @@ compress_pack_kernel(const __half* __restrict__ x, int64_t tokens, const int64_t
     __syncthreads();
     const uint32_t lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    const uint32_t above = lane == 0 ? 0u : (0xffffffffu << (32 - lane));  // bits of elements before mine
-    const uint32_t mybit = 0x80000000u >> lane;
+    const uint32_t above = lane_above(lane), mybit = lane_bit(lane);
     const int64_t tile0 = static_cast<int64_t>(tb) * 128 + warp * 16;
     // one coalesced read of this warp's 16 bitmaps and 16 offsets
     uint64_t bm_l = 0;
@@ -301,8 +305,8 @@ __device__ __forceinline__ void compress_chunk_body(const ChunkArgs& a, int whic
     for (int i = 0; i < 16; ++i) {
         uint32_t e0, e1;
         tile_elems<LAYOUT>(blk, (t0 + i) & 127, lane, e0, e1);
-        const uint32_t hi = __brev(__ballot_sync(0xffffffffu, (e0 & 0x7fffu) != 0));
-        const uint32_t lo = __brev(__ballot_sync(0xffffffffu, (e1 & 0x7fffu) != 0));
+        const uint32_t hi = __ballot_sync(0xffffffffu, (e0 & 0x7fffu) != 0);
+        const uint32_t lo = __ballot_sync(0xffffffffu, (e1 & 0x7fffu) != 0);
         if (lane == static_cast<uint32_t>(i)) {
             my_hi = hi;
             my_lo = lo;
@@ -341,8 +345,7 @@ __device__ __forceinline__ void compress_chunk_body(const ChunkArgs& a, int whic
     }
     __syncthreads();
     // 4. pack: one contiguous (<= 128 B) store per tile
-    const uint32_t above = lane == 0 ? 0u : (0xffffffffu << (32 - lane));
-    const uint32_t mybit = 0x80000000u >> lane;
+    const uint32_t above = lane_above(lane), mybit = lane_bit(lane);
     uint16_t* out = reinterpret_cast<uint16_t*>(a.nz[which]) + a.head_base[which][h];
     uint32_t* st32 = reinterpret_cast<uint32_t*>(stage[warp]);
 #pragma unroll 2
@@ -490,15 +493,15 @@ __device__ __forceinline__ void prefill_block_body(const PrefillArgs& a, int whi
     // 2. bitmaps + padded counts + packing in ONE pass over the tile's elements: warp w owns tiles 16w .. 16w+15,
     //    lane i < 16 keeps the bitmap of tile 16w+i; every lane drops its two elements at their rank in the packing area
     const int t0 = warp * 16;
-    const uint32_t above = lane == 0 ? 0u : (0xffffffffu << (32 - lane));  // bits of elements before mine
+    const uint32_t above = lane_above(lane);  // bits of elements before mine
     uint32_t my_hi = 0, my_lo = 0;
 #pragma unroll 4
     for (int i = 0; i < 16; ++i) {
         uint32_t e0, e1;
         tile_elems<LAYOUT>(tile, t0 + i, lane, e0, e1);
         const bool nz0 = (e0 & 0x7fffu) != 0, nz1 = (e1 & 0x7fffu) != 0;
-        const uint32_t hi = __brev(__ballot_sync(0xffffffffu, nz0));
-        const uint32_t lo = __brev(__ballot_sync(0xffffffffu, nz1));
+        const uint32_t hi = __ballot_sync(0xffffffffu, nz0);
+        const uint32_t lo = __ballot_sync(0xffffffffu, nz1);
         if (nz0) stage[warp][i][__popc(hi & above)] = static_cast<uint16_t>(e0);
         if (nz1) stage[warp][i][__popc(hi) + __popc(lo & above)] = static_cast<uint16_t>(e1);
         if (lane == static_cast<uint32_t>(i)) {

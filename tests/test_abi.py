@@ -27,14 +27,14 @@ def test_every_declared_symbol_is_exported(lib):
     for name in declared:
         assert hasattr(raw, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
-    assert lib.mfb200_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.mfb200_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_struct_layout_matches_header():
     from mustafar_b200 import _lib
     # 12 x int32/float, then 8-byte fields only
     assert _lib.DecodeParams.q.offset == 48
-    assert C.sizeof(_lib.DecodeParams) == 48 + 22 * 8
+    assert C.sizeof(_lib.DecodeParams) == 48 + 25 * 8
     assert C.sizeof(_lib.PeerOut) == 24 + 2 * 8 * 8 and _lib.PeerOut.out.offset == 24
 
 

@@ -665,3 +665,45 @@ def test_properties_full_size_config3_shape():
             row = torch.from_numpy(O.prune_rows(row.cpu().numpy(), 0.7)).cuda()
         want = row[:, :, None, :].expand(b, hkv, groups, 128).reshape(b, hkv * groups, 1, 128)
         assert torch.allclose(o.float(), want.float(), atol=1e-3, rtol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,hkv,groups,T,shared_row", [(2, 4, 1, 790, False), (3, 2, 4, 1310, False), (1, 8, 2, 545, True),
+                                                        (2, 1, 8, 400, True)])
+def test_fused_rotary_embedding_is_bit_identical_to_rotating_first(b, hkv, groups, T, shared_row):
+    """mfb200_decode_params::rope_cos (the apply_rotary_pos_emb of llama_mustafar_kernel.py:238-253 inside the attention
+    launch): decode steps fed UNROTATED q / k with (cos, sin) must produce the same bits - outputs and appended window rows -
+    as steps fed the fp16 tensors transformers' apply_rotary_pos_emb computes, across a compression event."""
+    from transformers.models.llama.modeling_llama import apply_rotary_pos_emb
+    from mustafar_b200.attention import MustafarKVCache
+    torch.manual_seed(T)
+    k0 = torch.randn(b, hkv, T, 128, device="cuda", dtype=torch.float16)
+    v0 = torch.randn(b, hkv, T, 128, device="cuda", dtype=torch.float16)
+    caches = [MustafarKVCache(b, hkv, groups, T + 64, 0.5, 0.5) for _ in range(2)]
+    for c in caches:
+        c.prefill(k0, v0)
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, 128, 2, device="cuda").float() / 128))
+    steps = 40
+    for t in range(steps):
+        pos = torch.full((1 if shared_row else b, 1), T + t, device="cuda") + (0 if shared_row else torch.arange(b, device="cuda")[:, None] * 3)
+        freqs = pos.float()[:, :, None] * inv_freq[None, None, :]
+        emb = torch.cat((freqs, freqs), dim=-1)
+        cos, sin = emb.cos().half(), emb.sin().half()  # [B or 1, 1, 128]
+        q = torch.randn(b, hkv * groups, 1, 128, device="cuda", dtype=torch.float16)
+        k = torch.randn(b, hkv, 1, 128, device="cuda", dtype=torch.float16)
+        v = torch.randn(b, hkv, 1, 128, device="cuda", dtype=torch.float16)
+        q_rot, k_rot = apply_rotary_pos_emb(q, k, cos, sin)
+        want = caches[0].decode_step(q_rot, k_rot, v)
+        got = caches[1].decode_step(q, k, v, rope=(cos, sin))
+        assert torch.equal(got, want), (t, (got.float() - want.float()).abs().max().item())
+        # a step without rope right after one with it must not inherit the fields
+        assert not caches[1]._p.rope_cos and not caches[1]._p.rope_sin
+    assert caches[0].comp_len == caches[1].comp_len and caches[0].win_len == caches[1].win_len
+    n = caches[0].win_len
+    assert torch.equal(caches[0].k_win[:, :n], caches[1].k_win[:, :n]) and torch.equal(caches[0].v_win[:, :n], caches[1].v_win[:, :n])
+    # the compressed streams were built from those window rows (the steps after the compression event attend over them)
+    tiles = caches[0].comp_len * 2
+    assert torch.equal(caches[0].k.bmp[:, :tiles], caches[1].k.bmp[:, :tiles])
+    assert torch.equal(caches[0].k.idx[:, :tiles + 1], caches[1].k.idx[:, :tiles + 1])
+    with pytest.raises(ValueError):
+        caches[1].decode_step(q, k, v, rope=(cos.float(), sin.float()))

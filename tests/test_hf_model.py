@@ -99,3 +99,70 @@ def test_llama_decode_matches_masked_dense(family, heads, hkv, sparsity):
     # fp16 model, two layers: attention outputs agree to ~2.5e-4 (test_gpu_parity), logits to ~1e-3 of their range
     assert d.max().item() <= 2e-2 * scale and d.mean().item() <= 2e-3 * scale, (d.max().item(), d.mean().item(), scale)
     assert (got.argmax(-1) == ref.argmax(-1)).float().mean().item() > 0.97
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("heads,hkv,batch", [(2, 2, 2), (4, 1, 3)])
+def test_graphed_decoder_equals_eager_steps(heads, hkv, batch):
+    """`GraphedDecoder` (whole decode step = one CUDA-graph replay, device-side window lengths) against the same model stepped
+    eagerly through `MustafarCache`, teacher forced, across a compression event (window 44 -> 288 -> 32) and the re-capture."""
+    import mustafar_b200.hf as mhf
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(vocab_size=512, hidden_size=128 * heads, intermediate_size=512, num_hidden_layers=3, num_attention_heads=heads,
+                      num_key_value_heads=hkv, head_dim=128, max_position_embeddings=2048)
+    torch.manual_seed(0)
+    model = LlamaForCausalLM(cfg).half().cuda().eval()
+    model.config._attn_implementation = mhf.ATTN_NAME
+    T0, steps = 300, 270
+    ids = torch.randint(0, cfg.vocab_size, (batch, T0 + steps), generator=torch.Generator().manual_seed(2)).cuda()
+
+    eager_cache = mhf.MustafarCache(cfg, 0.5, 0.5, max_tokens=T0 + steps + 8)
+    ref = []
+    with torch.no_grad():
+        model(input_ids=ids[:, :T0], past_key_values=eager_cache, use_cache=True)
+        for t in range(T0, T0 + steps):
+            ref.append(model(input_ids=ids[:, t:t + 1], past_key_values=eager_cache, use_cache=True).logits[:, -1].float())
+    ref = torch.stack(ref)
+
+    cache = mhf.MustafarCache(cfg, 0.5, 0.5, max_tokens=T0 + steps + 8)
+    dec = mhf.GraphedDecoder(model, cache, max_new_tokens=steps + 1)
+    dec.prefill(ids[:, :T0])
+    got = torch.stack([dec.step(ids[:, t:t + 1]).float().clone() for t in range(T0, T0 + steps)])
+    kv, kv_e = cache.layers[0].kv, eager_cache.layers[0].kv
+    assert dec.captures == 2  # once after the prefill, once after the compression at T = 544
+    assert (kv.comp_len, kv.win_len) == (kv_e.comp_len, kv_e.win_len) == (512, T0 + steps - 512)
+    assert cache.get_seq_length() == T0 + steps
+    # the caches must hold the same bytes: same appended rows, same compression
+    for l, le in zip(cache.layers, eager_cache.layers):
+        assert torch.equal(l.kv.k_win[:, :kv.win_len], le.kv.k_win[:, :kv.win_len])
+        assert torch.equal(l.kv.v.bmp[:, :1024], le.kv.v.bmp[:, :1024])
+    d = (got - ref).abs()
+    scale = ref.abs().max().item()
+    # same kernels, another split plan (planned for the window's capacity): fp32 merge-order noise only
+    assert d.max().item() <= 5e-3 * scale, (d.max().item(), scale)
+    # the chosen tokens were recorded on the device: slot t holds argmax of step t's logits
+    assert torch.equal(dec.tokens[:, 1:steps + 1], got.argmax(-1).T)
+
+
+@pytest.mark.gpu
+def test_graphed_decoder_generate_matches_hf_generate():
+    import mustafar_b200.hf as mhf
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                      num_key_value_heads=2, head_dim=128, max_position_embeddings=2048)
+    torch.manual_seed(3)
+    model = LlamaForCausalLM(cfg).half().cuda().eval()
+    model.config._attn_implementation = mhf.ATTN_NAME
+    ids = torch.randint(1, cfg.vocab_size, (2, 290), generator=torch.Generator().manual_seed(4)).cuda()
+    new = 40
+    with torch.no_grad():
+        want = model.generate(input_ids=ids, attention_mask=torch.ones_like(ids), max_new_tokens=new, do_sample=False,
+                              past_key_values=mhf.MustafarCache(cfg, 0.5, 0.5, max_tokens=400), eos_token_id=None, pad_token_id=0)
+    got = mhf.GraphedDecoder(model, mhf.MustafarCache(cfg, 0.5, 0.5, max_tokens=400), max_new_tokens=new).generate(ids, new)
+    assert got.shape == want.shape and torch.equal(got[:, :291], want[:, :291])  # the prefill's token is bit-identical
+    # a random-init model's logits are nearly flat, so one flipped near-tie changes the continuation: require a long common prefix
+    same = (got == want).all(0).float()
+    first_diff = int(same.argmin().item()) if same.min().item() == 0 else got.shape[1]
+    assert first_diff >= 290 + 8, first_diff
+    with pytest.raises(ValueError):
+        mhf.GraphedDecoder(model, mhf.MustafarCache(cfg, 0.5, 0.5, max_tokens=400), max_new_tokens=4).generate(ids, 5)

@@ -6,6 +6,9 @@ wall-clock around `model.generate`, then `torch.cuda.max_memory_allocated`), on 
 
 Arms (same weights, same prompt ids, greedy decoding, eos disabled):
   mustafar  attn_implementation="mustafar" + MustafarCache (this repo: fused append + sparse attention launch per layer)
+  mustafar_graph  the same model and cache through `mustafar_b200.hf.GraphedDecoder`: the whole decode step is ONE CUDA-graph replay
+  sdpa_graph      dense StaticCache + torch SDPA with the decode step captured the same way (the strongest dense baseline here:
+                  attention always spans the cache's full capacity, prompt + new + 64 tokens, behind a mask)
   sdpa      dense DynamicCache + torch SDPA
   flash     dense DynamicCache + flash_attention_2 (if transformers accepts the installed flash_attn)
   ref_cuda  the reference's decode glue (llama_mustafar_kernel.py:268-320) on the reference's own CUDA kernels built for
@@ -68,16 +71,65 @@ def register_ref_cuda():
     AttentionMaskInterface.register("mustafar_ref", sdpa_mask)
 
 
+class DenseGraphDecoder:
+    """Greedy decode of the stock model over a dense StaticCache with the decode step captured in a CUDA graph."""
+
+    def __init__(self, model, cache, capacity):
+        self.model, self.cache, self.capacity = model, cache, capacity
+        self.graph = None
+
+    @torch.no_grad()
+    def _body(self):
+        out = self.model(input_ids=self.ids, position_ids=self.pos, past_key_values=self.cache, use_cache=True)
+        nxt = out.logits[:, -1].argmax(-1, keepdim=True)
+        self.tokens.scatter_(1, self.slot, nxt)
+        self.ids.copy_(nxt)
+        self.pos.add_(1)
+        self.slot.add_(1)
+
+    @torch.no_grad()
+    def generate(self, ids, new):
+        b, t = ids.shape
+        dev = ids.device
+        out = self.model(input_ids=ids, past_key_values=self.cache, use_cache=True, logits_to_keep=1)
+        first = out.logits[:, -1].argmax(-1, keepdim=True)
+        self.ids, self.pos = first.clone(), torch.full((b, 1), t, dtype=torch.long, device=dev)
+        self.slot = torch.ones((b, 1), dtype=torch.long, device=dev)
+        self.tokens = torch.zeros((b, self.capacity), dtype=torch.long, device=dev)
+        self.tokens[:, :1] = first
+        if new > 1:
+            # warm-up step on a side stream (it really decodes one token), then capture and replay the rest
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            if new > 2:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._body()
+                # the capture ran `StaticLayer.update` on the host once without executing: nothing device-side moved
+                for _ in range(new - 2):
+                    g.replay()
+                self.graph = g
+        return torch.cat([ids, self.tokens[:, :new]], 1)
+
+
 def run_arm(model, arm, ids, new, k_sparsity, v_sparsity):
     import mustafar_b200.hf as mhf
     from transformers import DynamicCache
     b, t0 = ids.shape
-    impl = {"mustafar": "mustafar", "sdpa": "sdpa", "flash": "flash_attention_2", "ref_cuda": "mustafar_ref"}[arm]
+    impl = {"mustafar": "mustafar", "mustafar_graph": "mustafar", "sdpa": "sdpa", "sdpa_graph": "sdpa", "flash": "flash_attention_2",
+            "ref_cuda": "mustafar_ref"}[arm]
     model.config._attn_implementation = impl
 
     def make_cache():
-        if arm in ("mustafar", "ref_cuda"):
+        if arm in ("mustafar", "mustafar_graph", "ref_cuda"):
             return mhf.MustafarCache(model.config, k_sparsity, v_sparsity, max_tokens=t0 + new + 64)
+        if arm == "sdpa_graph":
+            from transformers import StaticCache
+            return StaticCache(config=model.config, max_cache_len=t0 + new + 64)
         return DynamicCache(config=model.config)
 
     def gen(n):
@@ -85,8 +137,15 @@ def run_arm(model, arm, ids, new, k_sparsity, v_sparsity):
         torch.cuda.synchronize()
         t = time.time()
         with torch.no_grad():
-            out = model.generate(input_ids=ids, attention_mask=torch.ones_like(ids), max_new_tokens=n, do_sample=False,
-                                 past_key_values=cache, eos_token_id=None, pad_token_id=0)
+            if arm == "mustafar_graph":
+                dec = mhf.GraphedDecoder(model, cache, max_new_tokens=max(n, 2))
+                out = dec.generate(ids, n)
+                cache._captures = dec.captures
+            elif arm == "sdpa_graph":
+                out = DenseGraphDecoder(model, cache, max(n, 2)).generate(ids, n)
+            else:
+                out = model.generate(input_ids=ids, attention_mask=torch.ones_like(ids), max_new_tokens=n, do_sample=False,
+                                     past_key_values=cache, eos_token_id=None, pad_token_id=0)
         torch.cuda.synchronize()
         return time.time() - t, out, cache
 
@@ -102,10 +161,13 @@ def run_arm(model, arm, ids, new, k_sparsity, v_sparsity):
     peak = torch.cuda.max_memory_allocated()
     held = cache.bytes_held() if hasattr(cache, "bytes_held") else sum(
         l.keys.numel() * 2 + l.values.numel() * 2 for l in cache.layers if getattr(l, "keys", None) is not None)
+    captures = getattr(cache, "_captures", None)
     dec = (tn - t1) / max(new - 1, 1)
     res = {"arm": arm, "prefill_s": round(t1, 4), "total_s": round(tn, 3), "decode_ms_per_token": round(dec * 1e3, 3),
            "decode_tok_s_per_seq": round(1.0 / dec, 2), "decode_tok_s_aggregate": round(b / dec, 2),
            "peak_allocated_GB": round(peak / 2**30, 3), "allocated_before_GB": round(base / 2**30, 3), "kv_bytes_held_GB": round(held / 2**30, 3)}
+    if captures is not None:
+        res["graph_captures"] = captures  # capture time is inside decode_ms_per_token
     del cache
     mhf._ACTIVE.cache = None
     return res, out
@@ -119,7 +181,7 @@ def main():
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--kv-heads", type=int, default=32)
     ap.add_argument("--sparsity", type=float, default=0.5)
-    ap.add_argument("--arms", default="mustafar,flash,ref_cuda")
+    ap.add_argument("--arms", default="mustafar_graph,mustafar,sdpa_graph,flash,ref_cuda")
     ap.add_argument("--json", default="")
     a = ap.parse_args()
     import mustafar_b200.hf  # noqa: F401  registers "mustafar"
@@ -141,7 +203,7 @@ def main():
             res, toks = run_arm(model, arm, ids, a.new, a.sparsity, a.sparsity)
         except Exception as e:
             res, toks = {"arm": arm, "unavailable": f"{type(e).__name__}: {e}"[:200]}, None
-        if toks is not None and arm in ("mustafar", "ref_cuda"):
+        if toks is not None and arm in ("mustafar", "mustafar_graph", "ref_cuda"):
             if ref_tokens is None:
                 ref_tokens = toks
             else:  # same cache contents, two attention implementations; a random-init model's near-flat logits flip on 1e-4
