@@ -11,6 +11,8 @@
  * Reference interfaces each entry point replaces (paths relative to /root/reference):
  *
  *   mfb200_prune_rows            models/llama_mustafar_kernel.py:77-113, :117-153  (dh_prune_key/value)
+ *   mfb200_prune_rows_scored     models/llama_mustafar_Kt_Opa_Vt_Mag.py:98-106, :131-156 (output-aware dh_prune_key)
+ *   mfb200_prune_token_groups    models/llama_mustafar_Kt_Mag_Vc_Mag.py:107-170 (channel-wise dh_prune_value)
  *   mfb200_compress_count        kernel/compression.py:9-54, :57-115   (calculate_bitmap_{key,value}_batched)
  *   mfb200_compress_scan         kernel/compression.py:294-304, :387-397 (torch.cumsum / cat glue)
  *   mfb200_compress_pack         kernel/compression.py:118-174, :178-247 (compress_{key,value}_batched)
@@ -59,6 +61,20 @@ const char* mfb200_last_error(void);
  * y[r, :] = x[r, :] * (|x[r, :]| >= kth_smallest(|x[r, :]|, k)),  rows of 128 fp16.
  * k = max(1, int(sparsity*128)) is computed by the caller.  x == y (in place) is allowed. */
 int mfb200_prune_rows(const void* x, void* y, int64_t rows, int k, mfb200_stream_t stream);
+
+/* ---- f4: the other pruning policies that feed the same compressed format -----------------------
+ * Output-aware key pruning (models/llama_mustafar_Kt_Opa_Vt_Mag.py:98-106 prefill, :131-156 decode):
+ *   score[r, c] = | x[r, c] * w[r / rows_per_unit, c] |  (fp16 product),  w: fp16 [units, 128] = the unit's folded |q|;
+ *   y[r, :] = x[r, :] * (score[r, :] >= kth_smallest(score[r, :], k)),  k = 128 - n_keep + 1 for n_keep survivors.
+ *   rows_per_unit == 0: w is fp16 [rows, 128] and IS the (non-negative) score - the decode-time form, where the score of the
+ *   oldest window row has been accumulated over group_size steps (`:131-145`).
+ *   Equal to the reference's sort + scatter mask unless the n_keep-th and (n_keep+1)-th highest scores tie (it then keeps an
+ *   arbitrary subset of the tied entries; here all of them survive).  x == y allowed. */
+int mfb200_prune_rows_scored(const void* x, const void* w, void* y, int64_t rows, int64_t rows_per_unit, int k, mfb200_stream_t stream);
+/* Channel-wise value pruning (models/llama_mustafar_Kt_Mag_Vc_Mag.py:107-170): x fp16 [units, tokens, 128], tokens % group == 0,
+ * group <= 128; inside every group of `group` consecutive tokens each channel keeps |x| >= the k-th smallest magnitude of its
+ * `group` values (k = max(1, int(sparsity*group)) is computed by the caller).  x == y allowed. */
+int mfb200_prune_token_groups(const void* x, void* y, int64_t units, int64_t tokens, int group, int k, mfb200_stream_t stream);
 
 /* ---- a2/a3: bitmaps + padded per-tile counts ----------------------------------------------------
  * x: fp16 [heads, tokens, 128] contiguous, tokens % 64 == 0.  If prune_k > 0 the threshold prune of

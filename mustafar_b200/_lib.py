@@ -64,6 +64,8 @@ SIGNATURES = {
     "mfb200_abi_version": (_i32, []),
     "mfb200_last_error": (C.c_char_p, []),
     "mfb200_prune_rows": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "mfb200_prune_rows_scored": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp]),
+    "mfb200_prune_token_groups": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "mfb200_compress_count": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     "mfb200_compress_scan": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp]),
     "mfb200_compress_pack": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),

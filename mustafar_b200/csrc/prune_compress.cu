@@ -94,6 +94,61 @@ __global__ void __launch_bounds__(256) prune_rows_kernel(const uint2* __restrict
     y[row * 32 + lane] = prune4(v, k);
 }
 
+// ---- other pruning policies feeding the same format ------------------------------------------
+// Output-aware key pruning (models/llama_mustafar_Kt_Opa_Vt_Mag.py:98-106, :131-156): the score of element c of a row is
+// |x[c] * w[c]| (an fp16 product, as the reference's fp16 tensor ops compute it), w = the unit's folded |q|; the n_keep
+// highest scores survive.  Threshold form: keep score >= the k-th smallest score, k = 128 - n_keep + 1 - the reference's
+// sort + scatter keeps the same set whenever the n_keep-th and (n_keep+1)-th highest scores differ; when they tie it keeps an
+// arbitrary subset of the tied elements (torch.sort is not stable), here every tied element survives.
+__global__ void __launch_bounds__(256) prune_rows_scored_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w,
+                                                                uint2* __restrict__ y, int64_t rows, int64_t rows_per_unit, int k) {
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const uint32_t lane = lane_id();
+    const uint2 v = x[row * 32 + lane];
+    uint32_t kx, ky;
+    if (rows_per_unit > 0) {  // score = |x * w[unit]|
+        const uint2 ww = w[(row / rows_per_unit) * 32 + lane];
+        const __half2 s0 = __hmul2_rn(*reinterpret_cast<const __half2*>(&v.x), *reinterpret_cast<const __half2*>(&ww.x));
+        const __half2 s1 = __hmul2_rn(*reinterpret_cast<const __half2*>(&v.y), *reinterpret_cast<const __half2*>(&ww.y));
+        kx = *reinterpret_cast<const uint32_t*>(&s0) & 0x7fff7fffu, ky = *reinterpret_cast<const uint32_t*>(&s1) & 0x7fff7fffu;
+    } else {  // the caller's own score rows (the decode-time form: an accumulated score, `:131-145`)
+        const uint2 sc = w[row * 32 + lane];
+        kx = sc.x & 0x7fff7fffu, ky = sc.y & 0x7fff7fffu;
+    }
+    const uint32_t tb = warp_kth_smallest(kx, ky, k) * 0x10001u;
+    const uint32_t gx = ((kx | 0x80008000u) - tb) & 0x80008000u, gy = ((ky | 0x80008000u) - tb) & 0x80008000u;
+    y[row * 32 + lane] = make_uint2(v.x & ((gx - (gx >> 15)) | 0x80008000u), v.y & ((gy - (gy >> 15)) | 0x80008000u));
+}
+
+// Channel-wise value pruning (models/llama_mustafar_Kt_Mag_Vc_Mag.py:107-170): inside every group of `group` consecutive
+// tokens, each CHANNEL keeps the entries with |x| >= the k-th smallest magnitude of that channel's `group` values.
+// One CTA of 128 threads per (unit, group); thread c owns channel c: bitwise bisection of the 15-bit magnitude over the
+// column held in shared memory (a warp reads 64 contiguous bytes per token: conflict-free).
+constexpr int kMaxGroupTokens = 128;  // 32 KB of static shared memory
+__global__ void __launch_bounds__(128) prune_token_groups_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t tokens,
+                                                                 int group, int k) {
+    __shared__ __align__(16) uint16_t tile[kMaxGroupTokens * kHeadDim];
+    const int64_t base = (static_cast<int64_t>(blockIdx.y) * tokens + static_cast<int64_t>(blockIdx.x) * group) * (kHeadDim / 8);
+    const int n16 = group * (kHeadDim / 8);
+    for (int i = threadIdx.x; i < n16; i += 128) reinterpret_cast<uint4*>(tile)[i] = x[base + i];
+    __syncthreads();
+    const int c = threadIdx.x;
+    uint32_t t = 0;
+    for (int bit = 14; bit >= 0; --bit) {  // largest t with count(key < t) < k  ==  the k-th smallest
+        const uint32_t cand = t | (1u << bit);
+        int cnt = 0;
+        for (int r = 0; r < group; ++r) cnt += (tile[r * kHeadDim + c] & 0x7fffu) < cand ? 1 : 0;
+        if (cnt < k) t = cand;
+    }
+    for (int r = 0; r < group; ++r) {
+        const uint16_t v = tile[r * kHeadDim + c];
+        tile[r * kHeadDim + c] = (v & 0x7fffu) >= t ? v : (v & 0x8000u);  // x * False = +-0
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n16; i += 128) y[base + i] = reinterpret_cast<const uint4*>(tile)[i];
+}
+
 // Loads one 64-token block of head h into smem (pitch kPitch), pruning on the fly if prune_k > 0.
 __device__ __forceinline__ void load_block(const __half* __restrict__ x, int64_t tokens, int64_t h, int tb,
                                            int prune_k, uint16_t* tile) {
@@ -589,6 +644,33 @@ extern "C" int mfb200_prune_rows(const void* x, void* y, int64_t rows, int k, mf
     prune_rows_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint2*>(x), static_cast<uint2*>(y), rows, k);
     return launch_status("prune_rows_kernel");
+}
+
+extern "C" int mfb200_prune_rows_scored(const void* x, const void* w, void* y, int64_t rows, int64_t rows_per_unit, int k,
+                                        mfb200_stream_t stream) {
+    MFB_REQUIRE(x && w && y, "prune_rows_scored: null pointer");
+    MFB_REQUIRE(k >= 1 && k <= kHeadDim, "prune_rows_scored: k=%d out of [1,128]", k);
+    MFB_REQUIRE(rows >= 0 && rows_per_unit >= 0, "prune_rows_scored: rows < 0 or rows_per_unit < 0");
+    MFB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 7) == 0,
+                "prune_rows_scored: pointers must be 8-byte aligned");
+    if (rows == 0) return MFB200_OK;
+    prune_rows_scored_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint2*>(x), static_cast<const uint2*>(w), static_cast<uint2*>(y), rows, rows_per_unit, k);
+    return launch_status("prune_rows_scored_kernel");
+}
+
+extern "C" int mfb200_prune_token_groups(const void* x, void* y, int64_t units, int64_t tokens, int group, int k, mfb200_stream_t stream) {
+    MFB_REQUIRE(x && y, "prune_token_groups: null pointer");
+    MFB_REQUIRE(group >= 1 && group <= kMaxGroupTokens, "prune_token_groups: group=%d out of [1,%d]", group, kMaxGroupTokens);
+    MFB_REQUIRE(k >= 1 && k <= group, "prune_token_groups: k=%d out of [1,group]", k);
+    MFB_REQUIRE(units >= 0 && units <= 65535 && tokens >= 0 && tokens % group == 0,
+                "prune_token_groups: tokens=%lld must be a multiple of group=%d (units <= 65535)", static_cast<long long>(tokens), group);
+    MFB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, "prune_token_groups: pointers must be 16-byte aligned");
+    if (units == 0 || tokens == 0) return MFB200_OK;
+    const dim3 grid(static_cast<unsigned>(tokens / group), static_cast<unsigned>(units));
+    prune_token_groups_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y),
+                                                                                     tokens, group, k);
+    return launch_status("prune_token_groups_kernel");
 }
 
 extern "C" int mfb200_compress_count(const void* x, int64_t heads, int64_t tokens, int layout, int prune_k,

@@ -59,6 +59,73 @@ def prune_rows(x: np.ndarray, sparsity: float) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------
+# f4. the other pruning policies (they only change the mask; format and kernels are the same)
+# ----------------------------------------------------------------------------
+def fold_queries(q: np.ndarray, groups: int, group_size=None) -> np.ndarray:
+    """[B, Hq, T, D] fp16 -> [B, Hkv, D] fp16 channel weights of the output-aware policy.
+
+    models/llama_mustafar_Kt_Opa_Vt_Mag.py:98-100 (prefill: mean of |q| over the last group_size tokens, then the sum over
+    the KV head's query heads) and :131-132 (decode, T == 1: |q| summed over the query heads).  torch reduces fp16 tensors
+    with an fp32 accumulator and rounds once per reduction; so does this."""
+    assert q.dtype == np.float16
+    b, hq, t, d = q.shape
+    a = np.abs(q if group_size is None else q[:, :, -group_size:, :])
+    folded = a.astype(np.float32).mean(axis=-2).astype(np.float16)
+    return folded.reshape(b, hq // groups, groups, d).astype(np.float32).sum(axis=-2).astype(np.float16)
+
+
+def prune_rows_scored(x: np.ndarray, w: np.ndarray, n_keep: int, keep_last: int = 0) -> np.ndarray:
+    """Output-aware key pruning, threshold form.  x [B, H, T, D]; w [B, H, D] (score = |x*w|, an fp16 product:
+    llama_mustafar_Kt_Opa_Vt_Mag.py:104) or [B, H, T, D] (w is the score: the accumulated decode-time score, :131-145).
+
+    The reference sorts the scores descending and scatters True at the first n_keep indices (:106-109, :139-150); that is
+    `score >= n_keep-th highest score` whenever that score differs from the next one.  On a tie at the cut the reference's
+    choice among the tied entries is implementation-defined (torch.sort is not stable); this restatement - and the CUDA
+    path - keeps all of them.  Dropped entries become x * False = +-0; the last keep_last tokens stay dense (:110)."""
+    assert x.dtype == np.float16 and w.dtype == np.float16
+    b, h, t, d = x.shape
+    score = np.abs(x * w[:, :, None, :]) if w.ndim == 3 else np.abs(w)
+    assert score.dtype == np.float16
+    thr = np.partition(score, d - n_keep, axis=-1)[..., d - n_keep : d - n_keep + 1]  # the n_keep-th highest
+    out = x * (score >= thr).astype(np.float16)
+    if keep_last:
+        out[:, :, -keep_last:, :] = x[:, :, -keep_last:, :]
+    return out
+
+
+def _bits16(a):
+    return np.ascontiguousarray(a).view(np.uint16)
+
+
+def check_scored_rows(got, want, x, score, n_keep, tied):
+    """Rows without a tie at the cut: bit-exact.  Tied rows: the reference keeps an arbitrary n_keep of the candidates; the
+    threshold form keeps every entry whose score reaches the cut - a superset that differs only in tied entries."""
+    got, want, x, score = (a.reshape(-1, a.shape[-1]) for a in (got, want, x, score))
+    tied = tied.reshape(-1)
+    assert np.array_equal(_bits16(got[~tied]), _bits16(want[~tied]))
+    for r in np.nonzero(tied)[0]:
+        thr = np.sort(score[r].astype(np.float32))[::-1][n_keep - 1]
+        keep = score[r].astype(np.float32) >= thr
+        assert np.array_equal(_bits16(got[r]), _bits16(x[r] * keep.astype(np.float16)))
+        ref_keep = (_bits16(want[r]) & 0x7fff) != 0
+        assert not np.any(ref_keep & ~keep) and keep.sum() > n_keep  # the reference's survivors are among ours
+
+
+def prune_token_groups(x: np.ndarray, sparsity: float, group_size: int = 32) -> np.ndarray:
+    """Channel-wise value pruning, models/llama_mustafar_Kt_Mag_Vc_Mag.py:107-170: in every group of group_size consecutive
+    tokens each channel keeps |v| >= its k-th smallest magnitude, k = max(1, int(sparsity * group_size)) (:142-153)."""
+    assert x.dtype == np.float16 and 0 <= sparsity <= 1
+    b, h, t, d = x.shape
+    if t % group_size != 0:
+        raise ValueError("Token dimension must be a multiple of group_size")
+    k = max(1, int(sparsity * group_size))
+    g = x.reshape(b, h, t // group_size, group_size, d)
+    mag = np.abs(g)
+    thr = np.partition(mag, k - 1, axis=3)[:, :, :, k - 1 : k, :]
+    return (g * (mag >= thr).astype(np.float16)).reshape(x.shape)
+
+
+# ----------------------------------------------------------------------------
 # a2-a6. bitmap + packed-nonzero format
 # ----------------------------------------------------------------------------
 def _tiles_key(x: np.ndarray) -> np.ndarray:

@@ -707,3 +707,92 @@ def test_fused_rotary_embedding_is_bit_identical_to_rotating_first(b, hkv, group
     assert torch.equal(caches[0].k.idx[:, :tiles + 1], caches[1].k.idx[:, :tiles + 1])
     with pytest.raises(ValueError):
         caches[1].decode_step(q, k, v, rope=(cos.float(), sin.float()))
+
+
+# --------------------------------------------------------------------------- f4: the other pruning policies
+POLICY_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["policy_opa_mha_s50", "policy_opa_gqa4_s70"])
+def test_output_aware_key_pruning_golden_and_oracle(name):
+    """mfb200_prune_rows_scored against the vectors the reference's own dh_prune_key produced
+    (llama_mustafar_Kt_Opa_Vt_Mag.py:65-178, oracle/make_golden_policies.py) and against the oracle on a larger case."""
+    from mustafar_b200 import pruning
+    check_scored_rows = O.check_scored_rows
+    g = np.load(os.path.join(POLICY_GOLDEN, name + ".npz"))
+    s, gs, groups = float(g["sparsity"]), int(g["group_size"]), int(g["groups"])
+    n_keep = int(128 * (1 - s))
+    key, q = torch.from_numpy(g["key"]).cuda(), torch.from_numpy(g["q"]).cuda()
+    w = pruning.fold_queries(q, groups, gs)
+    assert np.allclose(w.float().cpu().numpy(), g["w"].astype(np.float32), rtol=2e-3, atol=0)
+    # the prune itself on the reference's own weights: bit-exact off the tied rows, the documented superset on them
+    got = pruning.prune_rows_scored(key, torch.from_numpy(g["w"]).cuda(), n_keep, keep_last=gs).cpu().numpy()
+    tied = g["tied_rows"].copy()
+    tied[:, :, -gs:] = False
+    check_scored_rows(got, g["pruned"], g["key"], np.abs(g["key"] * g["w"][:, :, None, :]), n_keep, tied)
+    assert np.array_equal(_bits(got), _bits(O.prune_rows_scored(g["key"], g["w"], n_keep, keep_last=gs)))
+    for t in range(g["dec_window"].shape[0]):  # decode form: explicit score rows
+        oldest = g["dec_window"][t][:, :, :1, :]
+        sc = g["dec_acc_before"][t][:, :, 0:1, :] / np.float16(gs)
+        got = pruning.prune_rows_scored(torch.from_numpy(oldest).cuda(), torch.from_numpy(sc).cuda(), n_keep).cpu().numpy()
+        check_scored_rows(got, g["dec_pruned"][t], oldest, sc, n_keep, g["dec_tied"][t])
+    # the public entry point end to end, larger than the golden case, against the oracle fed the same folded weights
+    b, hkv, t = 2, 4, 1000
+    key = _randn((b, hkv, t, 128), 77).cuda()
+    q = _randn((b, hkv * groups, t, 128), 78).cuda()
+    got = pruning.dh_prune_key_output_aware(key, q, s, groups, gs)
+    w = pruning.fold_queries(q, groups, gs)
+    want = O.prune_rows_scored(key.cpu().numpy(), w.cpu().numpy(), n_keep, keep_last=gs)
+    assert np.array_equal(_bits(got.cpu().numpy()), _bits(want))
+    kept = np.count_nonzero(got[:, :, :-gs].cpu().numpy()) / got[:, :, :-gs].numel()
+    assert abs(kept - n_keep / 128) < 2e-3
+
+
+@pytest.mark.gpu
+def test_channelwise_value_pruning_golden_and_oracle():
+    """mfb200_prune_token_groups against the reference's own dh_prune_value (llama_mustafar_Kt_Mag_Vc_Mag.py:107-170)."""
+    from mustafar_b200 import pruning
+    for path in sorted(glob.glob(os.path.join(POLICY_GOLDEN, "policy_vc_*.npz"))):
+        g = np.load(path)
+        got = pruning.dh_prune_value_channelwise(torch.from_numpy(g["x"]).cuda(), float(g["sparsity"]), int(g["group_size"]))
+        assert np.array_equal(_bits(got.cpu().numpy()), _bits(g["y"])), path
+    x = _randn((3, 5, 32 * 37, 128), 5)
+    x[:, :, 100:140] = torch.round(x[:, :, 100:140] * 2) / 2  # ties, zeros and negative zeros
+    x[:, :, 200:232] = 0
+    for s, gs in ((0.5, 32), (0.7, 32), (0.9, 8), (0.25, 4), (1.0, 2)):
+        got = pruning.dh_prune_value_channelwise(x.cuda(), s, gs)
+        assert np.array_equal(_bits(got.cpu().numpy()), _bits(O.prune_token_groups(x.numpy(), s, gs))), (s, gs)
+    with pytest.raises(ValueError):
+        pruning.dh_prune_value_channelwise(x[:, :, :33].cuda(), 0.5, 32)
+    with pytest.raises(RuntimeError):
+        pruning.dh_prune_value_channelwise(x, 0.5, 32)  # CPU tensor: no fallback
+
+
+@pytest.mark.gpu
+def test_policy_pruned_cache_feeds_the_same_format_and_kernels():
+    """Kt_Opa_Vt_Mag / Kt_Mag_Vc_Mag end to end: keys pruned output-aware, values channel-wise, then the SAME compressed format
+    and attention launch (cache created with sparsity 0 = its own per-token prune is the identity)."""
+    from mustafar_b200 import pruning
+    from mustafar_b200.attention import MustafarKVCache
+    b, hkv, groups, T, s = 2, 2, 4, 800, 0.5
+    k, v = _randn((b, hkv, T, 128), 1), _randn((b, hkv, T, 128), 2)
+    qp = _randn((b, hkv * groups, T, 128), 3)
+    q = _randn((b, hkv * groups, 1, 128), 4)
+    L = O.compressed_length(T)
+    kp = pruning.dh_prune_key_output_aware(k[:, :, :L].cuda(), qp[:, :, :L].cuda(), s, groups, 32, keep_last=False)
+    vp = pruning.dh_prune_value_channelwise(v[:, :, :L].cuda(), s, 32)
+    k2, v2 = k.clone().cuda(), v.clone().cuda()
+    k2[:, :, :L], v2[:, :, :L] = kp, vp
+    cache = MustafarKVCache(b, hkv, groups, max_tokens=T + 300, k_sparsity=0.0, v_sparsity=0.0, nz_halves_per_token=88)
+    cache.prefill(k2, v2)
+    cache.check_overflow()
+    assert cache.comp_len == L
+    # the cache holds exactly the policy-pruned tensors
+    kc, _, vc, _, _, _ = cache.as_reference_tuple()
+    kd, vd = (x[:, :, :L].reshape(b * hkv, L, 128).cpu().numpy() for x in (k2, v2))
+    for got, (rb, ra, rp) in ((kc, O.convert_key_batched(kd)), (vc, O.convert_value_batched(vd))):
+        assert np.array_equal(got[0].cpu().numpy(), rb) and np.array_equal(got[1].cpu().numpy(), ra)
+        assert all(np.array_equal(_bits(a.cpu().numpy()), _bits(r)) for a, r in zip(got[2], rp))
+    got = cache.attend(q.cuda())
+    _check_attention(got, q, k2.cpu().numpy(), v2.cpu().numpy(), L)

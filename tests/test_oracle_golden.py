@@ -101,3 +101,47 @@ def test_compressed_length():
     assert O.compressed_length(300) == 256
     assert O.compressed_length(287) == 0
     assert O.compressed_length(5) == 0
+
+
+# ---- f4: the other pruning policies (golden vectors from the reference's own functions, oracle/make_golden_policies.py) ----
+POLICY_OPA = sorted(glob.glob(os.path.join(GOLDEN, "policy_opa_*.npz")))
+POLICY_VC = sorted(glob.glob(os.path.join(GOLDEN, "policy_vc_*.npz")))
+
+
+check_scored_rows = O.check_scored_rows
+
+
+def test_policy_golden_present():
+    assert len(POLICY_OPA) >= 2 and len(POLICY_VC) >= 5
+
+
+@pytest.mark.parametrize("path", POLICY_OPA, ids=[os.path.basename(p) for p in POLICY_OPA])
+def test_output_aware_key_pruning_matches_reference(path):
+    g = np.load(path)
+    s, gs, groups = float(g["sparsity"]), int(g["group_size"]), int(g["groups"])
+    n_keep = int(128 * (1 - s))
+    w = O.fold_queries(g["q"], groups, gs)
+    # the fold is two fp16 reductions: same values up to the last bit of the fp32 accumulation order
+    assert np.allclose(w.astype(np.float32), g["w"].astype(np.float32), rtol=2e-3, atol=0)
+    got = O.prune_rows_scored(g["key"], g["w"], n_keep, keep_last=gs)
+    score = np.abs(g["key"] * g["w"][:, :, None, :])
+    tied = g["tied_rows"].copy()
+    tied[:, :, -gs:] = False  # those rows stay dense whatever their scores
+    check_scored_rows(got, g["pruned"], g["key"], score, n_keep, tied)
+    assert np.array_equal(_bits(got[:, :, -gs:]), _bits(g["key"][:, :, -gs:]))
+    # decode form: the oldest window row, scored by its accumulated score / group_size (`:131-145`)
+    for t in range(g["dec_window"].shape[0]):
+        oldest = g["dec_window"][t][:, :, :1, :]
+        sc = g["dec_acc_before"][t][:, :, 0:1, :] / np.float16(gs)
+        assert sc.dtype == np.float16
+        got = O.prune_rows_scored(oldest, sc, n_keep)
+        check_scored_rows(got, g["dec_pruned"][t], oldest, sc, n_keep, g["dec_tied"][t])
+
+
+@pytest.mark.parametrize("path", POLICY_VC, ids=[os.path.basename(p) for p in POLICY_VC])
+def test_channelwise_value_pruning_matches_reference(path):
+    g = np.load(path)
+    y = O.prune_token_groups(g["x"], float(g["sparsity"]), int(g["group_size"]))
+    assert np.array_equal(_bits(y), _bits(g["y"]))
+    with pytest.raises(ValueError):
+        O.prune_token_groups(g["x"][:, :, :-1], float(g["sparsity"]), int(g["group_size"]))
