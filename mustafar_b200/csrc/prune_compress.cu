@@ -35,18 +35,17 @@ constexpr int kCompressThreads = 256;
 // turns the four flag bits into 0x00 / 0xFF bytes, IDP4A sums them (255 per hit), REDUX.SUM adds the lanes.
 // `u` carries threshold + this round's bias so that the bias costs no instruction of its own.
 // (A compare/select/add chain per key was 17 instructions per round and made the prune ALU-bound at 1.9 TB/s.)
-__device__ __forceinline__ uint32_t warp_kth_smallest(uint32_t kx, uint32_t ky, int k) {
+template <int START>
+__device__ __forceinline__ uint32_t kth_search(uint32_t u, uint32_t kx, uint32_t ky, uint32_t k255) {
     constexpr uint32_t kRep = 0x10001u;
-    // Round `bit` tests cand = t | 2^bit.  u = 0x8000 + cand - 1 in both fields; accepting the bit moves the next
+    // Round `bit` tests cand = t + 2^bit.  u = 0x8000 + cand - 1 in both fields; accepting the bit moves the next
     // round's u up by 2^(bit-1), rejecting it moves it down by 2^(bit-1) (fields never carry or borrow).
-    uint32_t u = 0x80008000u + ((1u << 14) - 1u) * kRep;
-    const uint32_t k255 = static_cast<uint32_t>(k) * 255u;
 #if MFB_SELECT_EARLY_EXIT
     const uint32_t km1_255 = k255 - 255u;
 #endif
     bool accept = false;
 #pragma unroll
-    for (int bit = 14; bit >= 0; --bit) {
+    for (int bit = START; bit >= 0; --bit) {
         uint32_t flags;
         asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(flags) : "r"(u - kx), "r"(u - ky));  // sign bytes of the 4 fields
         const uint32_t c255 = __reduce_add_sync(0xffffffffu, __dp4a(flags, 0x01010101u, 0u));
@@ -72,11 +71,54 @@ __device__ __forceinline__ uint32_t warp_kth_smallest(uint32_t kx, uint32_t ky, 
     return (u & 0x7fffu) + (accept ? 1u : 0u);  // round 0: u = 0x8000 + t
 }
 
+__device__ __forceinline__ uint32_t warp_kth_smallest(uint32_t kx, uint32_t ky, int k) {
+    return kth_search<14>(0x80008000u + ((1u << 14) - 1u) * 0x10001u, kx, ky, static_cast<uint32_t>(k) * 255u);
+}
+
+// The same k-th smallest, started from a HINT (the threshold of the previous token row of the same head: neighbouring
+// rows have neighbouring thresholds).  One double count checks that the answer lies in the 1024-wide window around the
+// hint - count(key < lo) < k <= count(key < lo + 1024), both counts in ONE REDUX (16-bit fields) - and the bisection then
+// only walks the window's 10 bits; any row whose threshold is elsewhere takes the full search.  Exact either way.
+#ifndef MFB_SELECT_HINT
+#define MFB_SELECT_HINT 1
+#endif
+#ifndef MFB_SELECT_NOINLINE
+#define MFB_SELECT_NOINLINE 1
+#endif
+constexpr uint32_t kNoHint = 0xffffffffu;
+#if MFB_SELECT_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+uint32_t warp_kth_smallest_near(uint32_t kx, uint32_t ky, int k, uint32_t hint) {
+    constexpr uint32_t kRep = 0x10001u;
+    const uint32_t k255 = static_cast<uint32_t>(k) * 255u;
+#if MFB_SELECT_HINT
+    if (hint <= 0x7fffu) {
+        const uint32_t lo = min(hint > 512u ? hint - 512u : 0u, 0x8000u - 1024u);
+        const uint32_t ua = (0x7fffu + lo) * kRep, ub = ua + 1024u * kRep;  // u of cand = lo and of cand = lo + 1024
+        uint32_t fa, fb;
+        asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(fa) : "r"(ua - kx), "r"(ua - ky));
+        asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(fb) : "r"(ub - kx), "r"(ub - ky));
+        const uint32_t c = __reduce_add_sync(0xffffffffu, __dp4a(fa, 0x01010101u, 0u) + (__dp4a(fb, 0x01010101u, 0u) << 16));
+        if ((c & 0xffffu) < k255 && (c >> 16) >= k255) return kth_search<9>(ua + 512u * kRep, kx, ky, k255);
+    }
+#endif
+    return kth_search<14>(0x80008000u + ((1u << 14) - 1u) * kRep, kx, ky, k255);
+}
+
 // Applies  x * (|x| >= thr)  to 4 halves packed in a uint2; dropped entries keep their sign bit
 // (fp16 x * 0 = +-0), exactly what `key_states_flat * mask` produces.
-__device__ __forceinline__ uint2 prune4(uint2 v, int k) {
+__device__ __forceinline__ uint2 prune4(uint2 v, int k, uint32_t* hint = nullptr) {
     const uint32_t kx = v.x & 0x7fff7fffu, ky = v.y & 0x7fff7fffu;
-    const uint32_t thr = warp_kth_smallest(kx, ky, k);
+    uint32_t thr;
+    if (hint != nullptr) {  // rows of one head in sequence: start from the previous row's threshold
+        thr = warp_kth_smallest_near(kx, ky, k, *hint);
+        *hint = thr;
+    } else {
+        thr = warp_kth_smallest(kx, ky, k);
+    }
     // per field: key >= thr  <=>  bit 15 of (0x8000 + key - thr); widen the flag to a keep mask, the sign bit always stays
     const uint32_t tb = thr * 0x10001u;
     const uint32_t gx = ((kx | 0x80008000u) - tb) & 0x80008000u, gy = ((ky | 0x80008000u) - tb) & 0x80008000u;
@@ -158,9 +200,10 @@ __device__ __forceinline__ void load_block(const __half* __restrict__ x, int64_t
     uint2 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = ldg_stream_v2(src + (warp * 8 + i) * 32 + lane);
+    uint32_t hint = kNoHint;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        if (prune_k > 0) v[i] = prune4(v[i], prune_k);
+        if (prune_k > 0) v[i] = prune4(v[i], prune_k, &hint);
         uint32_t* dst = reinterpret_cast<uint32_t*>(tile + (warp * 8 + i) * kPitch + 4 * lane);
         dst[0] = v[i].x;
         dst[1] = v[i].y;
@@ -343,9 +386,10 @@ __device__ __forceinline__ void compress_chunk_body(const ChunkArgs& a, int whic
         uint2 v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = ld_coherent_v2(src + (warp * 8 + i) * 32 + lane);
+        uint32_t hint = kNoHint;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            v[i] = prune4(v[i], a.prune_k[which]);
+            v[i] = prune4(v[i], a.prune_k[which], &hint);
             uint32_t* dst = reinterpret_cast<uint32_t*>(tile + (warp * 8 + i) * kPitch + 4 * lane);
             dst[0] = v[i].x;
             dst[1] = v[i].y;
@@ -530,9 +574,10 @@ __device__ __forceinline__ void prefill_block_body(const PrefillArgs& a, int whi
         uint2 v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = ldg_stream_v2(reinterpret_cast<const uint2*>(src + (warp * 8 + i) * a.stride_t[which]) + lane);
+        uint32_t hint = kNoHint;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if (a.prune_k[which] > 0) v[i] = prune4(v[i], a.prune_k[which]);
+            if (a.prune_k[which] > 0) v[i] = prune4(v[i], a.prune_k[which], &hint);
             uint32_t* dst = reinterpret_cast<uint32_t*>(tile + (warp * 8 + i) * kPitch + 4 * lane);
             dst[0] = v[i].x;
             dst[1] = v[i].y;
@@ -546,10 +591,13 @@ __device__ __forceinline__ void prefill_block_body(const PrefillArgs& a, int whi
     }
     __syncthreads();
     // 2. bitmaps + padded counts + packing in ONE pass over the tile's elements: warp w owns tiles 16w .. 16w+15,
-    //    lane i < 16 keeps the bitmap of tile 16w+i; every lane drops its two elements at their rank in the packing area
+    //    lane i < 16 keeps the bitmap of tile 16w+i; every lane drops its two elements at their rank in the packing area.
+    //    The 16 tiles of a warp are neighbours in the packed stream too, so they are packed back to back (`run` = the
+    //    warp-uniform fill level in halves, padded per tile) and leave as ONE contiguous run.
     const int t0 = warp * 16;
     const uint32_t above = lane_above(lane);  // bits of elements before mine
-    uint32_t my_hi = 0, my_lo = 0;
+    uint16_t* pack = &stage[warp][0][0];
+    uint32_t my_hi = 0, my_lo = 0, run = 0, my_end = 0;
 #pragma unroll 4
     for (int i = 0; i < 16; ++i) {
         uint32_t e0, e1;
@@ -557,26 +605,19 @@ __device__ __forceinline__ void prefill_block_body(const PrefillArgs& a, int whi
         const bool nz0 = (e0 & 0x7fffu) != 0, nz1 = (e1 & 0x7fffu) != 0;
         const uint32_t hi = __ballot_sync(0xffffffffu, nz0);
         const uint32_t lo = __ballot_sync(0xffffffffu, nz1);
-        if (nz0) stage[warp][i][__popc(hi & above)] = static_cast<uint16_t>(e0);
-        if (nz1) stage[warp][i][__popc(hi) + __popc(lo & above)] = static_cast<uint16_t>(e1);
+        const uint32_t pc_hi = __popc(hi);
+        if (nz0) pack[run + __popc(hi & above)] = static_cast<uint16_t>(e0);
+        if (nz1) pack[run + pc_hi + __popc(lo & above)] = static_cast<uint16_t>(e1);
+        run += (pc_hi + __popc(lo) + 7u) & ~7u;
         if (lane == static_cast<uint32_t>(i)) {
             my_hi = hi;
             my_lo = lo;
+            my_end = run;
         }
     }
     const int64_t tile_g = a.tile_offset + static_cast<int64_t>(tb) * 128 + t0 + lane;  // lanes < 16
-    int32_t cnt = 0;
-    if (lane < 16) {
-        a.bmp[which][u * a.bmp_stride + tile_g] = static_cast<int64_t>((static_cast<uint64_t>(my_hi) << 32) | my_lo);
-        cnt = ((__popc(my_hi) + __popc(my_lo) + 7) & ~7) >> 1;
-    }
-    int32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-        const int32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= static_cast<uint32_t>(o)) incl += n;
-    }
-    if (lane == 15) warp_tot[warp] = incl;
+    if (lane < 16) a.bmp[which][u * a.bmp_stride + tile_g] = static_cast<int64_t>((static_cast<uint64_t>(my_hi) << 32) | my_lo);
+    if (lane == 0) warp_tot[warp] = static_cast<int32_t>(run >> 1);  // counts are kept in units of 2 halves
     __syncthreads();
     // 3. this block's offset inside the unit's packed stream
     int32_t* idx = a.idx[which] + u * a.idx_stride;
@@ -595,20 +636,17 @@ __device__ __forceinline__ void prefill_block_body(const PrefillArgs& a, int whi
     __syncthreads();
     int32_t base = s_excl;
     for (int w = 0; w < warp; ++w) base += warp_tot[w];
-    if (lane < 16) idx[tile_g + 1] = base + incl;
-    const int32_t my_off = base + incl - cnt;  // lanes < 16: offset of tile t0 + lane (2-half units)
-    // 4. copy out: one contiguous (<= 128 B) store per tile
-    uint16_t* out = reinterpret_cast<uint16_t*>(a.nz[which]) + a.head_base[which][u];
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const int32_t o2 = __shfl_sync(0xffffffffu, my_off, i);
-        const uint32_t n_pad = 2u * static_cast<uint32_t>(__shfl_sync(0xffffffffu, cnt, i));  // halves
-        if (a.head_capacity > 0 && 2 * static_cast<int64_t>(o2) + n_pad > a.head_capacity) {
-            if (lane == 0 && a.overflow != nullptr) atomicExch(a.overflow, 1);
-        } else if (2 * lane < n_pad) {
-            reinterpret_cast<uint32_t*>(out + 2 * static_cast<int64_t>(o2))[lane] = reinterpret_cast<const uint32_t*>(stage[warp][i])[lane];
-        }
+    if (lane < 16) idx[tile_g + 1] = base + static_cast<int32_t>(my_end >> 1);
+    // 4. copy out the warp's run: 16-byte chunks (every tile start is 16-byte aligned relative to the unit's base)
+    uint16_t* out = reinterpret_cast<uint16_t*>(a.nz[which]) + a.head_base[which][u] + 2 * static_cast<int64_t>(base);
+    uint32_t chunks = run >> 3;
+    if (a.head_capacity > 0 && 2 * static_cast<int64_t>(base) + run > a.head_capacity) {
+        if (lane == 0 && a.overflow != nullptr) atomicExch(a.overflow, 1);
+        const int64_t room = a.head_capacity - 2 * static_cast<int64_t>(base);  // halves that still fit (never write past the slab)
+        chunks = room > 0 ? static_cast<uint32_t>(room >> 3) : 0u;
     }
+    __syncwarp();
+    for (uint32_t c = lane; c < chunks; c += 32) reinterpret_cast<uint4*>(out)[c] = reinterpret_cast<const uint4*>(pack)[c];
 }
 
 __global__ void __launch_bounds__(kCompressThreads) compress_prefill_kernel(const PrefillArgs a) {
@@ -803,6 +841,8 @@ extern "C" int mfb200_compress_prefill(const void* k, const void* v, const int64
     MFB_REQUIRE(tile_offset >= 0 && tile_offset % 128 == 0 && bmp_stride >= tile_offset + tokens * 2 && idx_stride >= tile_offset + tokens * 2 + 1,
                 "compress_prefill: cache slab too small for tile_offset=%lld", static_cast<long long>(tile_offset));
     MFB_REQUIRE(tokens / 64 <= 0x7fffffff, "compress_prefill: too many blocks");
+    MFB_REQUIRE(((reinterpret_cast<uintptr_t>(k_nz) | reinterpret_cast<uintptr_t>(v_nz)) & 15) == 0,
+                "compress_prefill: nonzero slabs must be 16-byte aligned (and every head base a multiple of 8 halves)");
     for (int w = 0; w < 2; ++w) {
         const int64_t* st = w ? v_strides : k_strides;
         MFB_REQUIRE((reinterpret_cast<uintptr_t>(w ? v : k) & 7) == 0 && st[0] % 4 == 0 && st[1] % 4 == 0 && st[2] % 4 == 0 && st[2] >= kHeadDim,
