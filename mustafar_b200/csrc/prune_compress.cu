@@ -127,13 +127,23 @@ __device__ __forceinline__ uint2 prune4(uint2 v, int k, uint32_t* hint = nullptr
     return make_uint2(v.x & keep_lo, v.y & keep_hi);
 }
 
+// One warp prunes kPruneRowsPerWarp consecutive token rows: all loads are issued first, and each select starts from the
+// previous row's threshold (warp_kth_smallest_near).
+constexpr int kPruneRowsPerWarp = 4;
 __global__ void __launch_bounds__(256) prune_rows_kernel(const uint2* __restrict__ x, uint2* __restrict__ y,
                                                          int64_t rows, int k) {
-    const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * kPruneRowsPerWarp;
+    if (row0 >= rows) return;
     const uint32_t lane = lane_id();
-    uint2 v = x[row * 32 + lane];
-    y[row * 32 + lane] = prune4(v, k);
+    const int n = static_cast<int>(min(static_cast<int64_t>(kPruneRowsPerWarp), rows - row0));
+    uint2 v[kPruneRowsPerWarp];
+#pragma unroll
+    for (int i = 0; i < kPruneRowsPerWarp; ++i)
+        if (i < n) v[i] = x[(row0 + i) * 32 + lane];
+    uint32_t hint = kNoHint;
+#pragma unroll
+    for (int i = 0; i < kPruneRowsPerWarp; ++i)
+        if (i < n) y[(row0 + i) * 32 + lane] = prune4(v[i], k, &hint);
 }
 
 // ---- other pruning policies feeding the same format ------------------------------------------
@@ -678,7 +688,7 @@ extern "C" int mfb200_prune_rows(const void* x, void* y, int64_t rows, int k, mf
     MFB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
                 "prune_rows: pointers must be 8-byte aligned");
     if (rows == 0) return MFB200_OK;
-    const int64_t grid = (rows + 7) / 8;
+    const int64_t grid = (rows + 8 * kPruneRowsPerWarp - 1) / (8 * kPruneRowsPerWarp);
     prune_rows_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint2*>(x), static_cast<uint2*>(y), rows, k);
     return launch_status("prune_rows_kernel");

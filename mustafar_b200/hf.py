@@ -275,6 +275,7 @@ class GraphedDecoder:
         self._graph = None
         self._stale = True  # the captured launches no longer match the cache (or nothing is captured yet)
         self.captures = 0
+        self.rope_fused = False
         self.ids = self.pos = self.slot = self.tokens = self.logits = None
 
     def _buffers(self, batch: int):
@@ -319,6 +320,7 @@ class GraphedDecoder:
             with torch.cuda.graph(g, pool=self._graph.pool() if self._graph is not None else None):
                 self.logits = self._body()
             self._graph, self._stale = g, False
+            self.rope_fused = st.rope is not None  # the rotary embedding runs inside the attention launches of this graph
             self._static_keepalive = st  # the graph's launches read st.lengths
             self.captures += 1
         finally:

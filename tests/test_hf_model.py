@@ -102,16 +102,22 @@ def test_llama_decode_matches_masked_dense(family, heads, hkv, sparsity):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("heads,hkv,batch", [(2, 2, 2), (4, 1, 3)])
-def test_graphed_decoder_equals_eager_steps(heads, hkv, batch):
+@pytest.mark.parametrize("family,heads,hkv,batch,fuse_rope", [("llama", 2, 2, 2, True), ("llama", 4, 1, 3, True),
+                                                              ("mistral", 4, 1, 2, True), ("llama", 2, 1, 1, False)])
+def test_graphed_decoder_equals_eager_steps(family, heads, hkv, batch, fuse_rope):
     """`GraphedDecoder` (whole decode step = one CUDA-graph replay, device-side window lengths) against the same model stepped
     eagerly through `MustafarCache`, teacher forced, across a compression event (window 44 -> 288 -> 32) and the re-capture."""
     import mustafar_b200.hf as mhf
-    from transformers import LlamaConfig, LlamaForCausalLM
-    cfg = LlamaConfig(vocab_size=512, hidden_size=128 * heads, intermediate_size=512, num_hidden_layers=3, num_attention_heads=heads,
-                      num_key_value_heads=hkv, head_dim=128, max_position_embeddings=2048)
+    if family == "llama":
+        from transformers import LlamaConfig as Config, LlamaForCausalLM as Model
+        extra = {}
+    else:
+        from transformers import MistralConfig as Config, MistralForCausalLM as Model
+        extra = {"sliding_window": None}
+    cfg = Config(vocab_size=512, hidden_size=128 * heads, intermediate_size=512, num_hidden_layers=3, num_attention_heads=heads,
+                 num_key_value_heads=hkv, head_dim=128, max_position_embeddings=2048, **extra)
     torch.manual_seed(0)
-    model = LlamaForCausalLM(cfg).half().cuda().eval()
+    model = Model(cfg).half().cuda().eval()
     model.config._attn_implementation = mhf.ATTN_NAME
     T0, steps = 300, 270
     ids = torch.randint(0, cfg.vocab_size, (batch, T0 + steps), generator=torch.Generator().manual_seed(2)).cuda()
@@ -125,11 +131,14 @@ def test_graphed_decoder_equals_eager_steps(heads, hkv, batch):
     ref = torch.stack(ref)
 
     cache = mhf.MustafarCache(cfg, 0.5, 0.5, max_tokens=T0 + steps + 8)
-    dec = mhf.GraphedDecoder(model, cache, max_new_tokens=steps + 1)
+    dec = mhf.GraphedDecoder(model, cache, max_new_tokens=steps + 1, fuse_rope=fuse_rope)
     dec.prefill(ids[:, :T0])
     got = torch.stack([dec.step(ids[:, t:t + 1]).float().clone() for t in range(T0, T0 + steps)])
     kv, kv_e = cache.layers[0].kv, eager_cache.layers[0].kv
     assert dec.captures == 2  # once after the prefill, once after the compression at T = 544
+    assert dec.rope_fused == fuse_rope  # the model file's apply_rotary_pos_emb was deferred to the attention launch (or not)
+    import sys
+    assert "deferred" not in sys.modules[type(model).__module__].apply_rotary_pos_emb.__name__  # and restored afterwards
     assert (kv.comp_len, kv.win_len) == (kv_e.comp_len, kv_e.win_len) == (512, T0 + steps - 512)
     assert cache.get_seq_length() == T0 + steps
     # the caches must hold the same bytes: same appended rows, same compression
