@@ -207,7 +207,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": config_dict(args.layers),
             "cpu_baseline": {"value": val, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -390,7 +390,7 @@ def run_ours(args):
         "build_s": t_build, "context_end": ctx_end, "local_batch": bl,
     }
     line.update(extras)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -665,8 +665,27 @@ def run_extras(args, world, rank, dev, timed, layer_params, launch_all, K):
     return out
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse()
+    # Libraries write to file descriptor 1 behind Python's back (NCCL prints "NCCL version ..." there when the first
+    # communicator comes up): keep the original stdout for the JSON line alone and send everything else to stderr.
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
