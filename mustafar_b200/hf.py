@@ -304,15 +304,16 @@ class GraphedDecoder:
         try:
             # dry run of every kernel of the step on a side stream (library handles, lazy module loading) with no effect on
             # the cache; the feedback buffers it overwrites are restored
-            keep = (self.ids.clone(), self.pos.clone(), self.slot.clone())
-            st.dry = True
-            side = torch.cuda.Stream(self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):
-                self._body()
-            torch.cuda.current_stream(self.device).wait_stream(side)
-            st.dry = False
-            self.ids.copy_(keep[0]); self.pos.copy_(keep[1]); self.slot.copy_(keep[2])
+            if self.captures == 0:  # re-captures after a compression launch the same kernels: nothing left to warm up
+                keep = (self.ids.clone(), self.pos.clone(), self.slot.clone())
+                st.dry = True
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    self._body()
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                st.dry = False
+                self.ids.copy_(keep[0]); self.pos.copy_(keep[1]); self.slot.copy_(keep[2])
             torch.cuda.current_stream(self.device).synchronize()
             # the previous capture stays alive until the new one exists: both live in one memory pool, whose blocks the new
             # capture reuses as soon as the old graph is dropped
