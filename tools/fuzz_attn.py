@@ -1,5 +1,5 @@
 """Randomised differential run of the fused decode attention against the fp32 torch oracle: python tools/fuzz_attn.py [cases] [seed]
-Random (batch, KV heads, G, context, sparsity, residual window, mask, forced plans), attend + a few fused decode steps each."""
+Random (batch, KV heads, G, context, sparsity, residual window, mask, forced plans, fused rotary embedding), attend + a few fused decode steps each."""
 import os, sys, random
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -38,8 +38,17 @@ def main():
                 o = c.attend(q, mask)
             else:
                 kn = torch.randn(b, hkv, 1, 128, device="cuda", generator=gen).half(); vn = torch.randn(b, hkv, 1, 128, device="cuda", generator=gen).half()
+                if rng.random() < 0.5:  # fused rotary embedding: the launch gets the unrotated rows, the oracle the rotated ones
+                    shared = rng.random() < 0.3
+                    ang = torch.rand(1 if shared else b, 1, 64, device="cuda", generator=gen) * 6.283
+                    cos, sin = torch.cat([ang, ang], -1).cos().half(), torch.cat([ang, ang], -1).sin().half()
+                    rot = lambda x: torch.cat([-x[..., 64:], x[..., :64]], -1)
+                    o = c.decode_step(q, kn, vn, rope=(cos, sin))
+                    q = q * cos.unsqueeze(1) + rot(q) * sin.unsqueeze(1)
+                    kn = kn * cos.unsqueeze(1) + rot(kn) * sin.unsqueeze(1)
+                else:
+                    o = c.decode_step(q, kn, vn)
                 k = torch.cat([k, kn], 2); v = torch.cat([v, vn], 2)
-                o = c.decode_step(q, kn, vn)
             L = c.comp_len if t == 0 or c.comp_len == L0 else c.comp_len
             L0 = c.comp_len
             # the oracle needs the pruned history as the cache holds it NOW (a compression event prunes 256 more rows)
