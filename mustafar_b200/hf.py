@@ -229,9 +229,11 @@ class _DeferredRope:
     def __enter__(self):
         if self.orig is None:
             return self
-        orig, step = self.orig, self.step
+        orig, step, owner = self.orig, self.step, threading.get_ident()
 
         def deferred(q, k, cos, sin, *args, **kwargs):
+            if threading.get_ident() != owner:  # the function is a module global: other threads keep the stock behaviour
+                return orig(q, k, cos, sin, *args, **kwargs)
             if (q.shape[-2] == 1 and k.shape[-2] == 1 and q.shape[-1] == HEAD_DIM and cos.shape[-1] == HEAD_DIM
                     and q.dtype == cos.dtype == sin.dtype == torch.float16 and cos.is_contiguous() and sin.is_contiguous()
                     and cos.numel() in (HEAD_DIM, q.shape[0] * HEAD_DIM)):
