@@ -60,6 +60,19 @@ def test_prune_vs_oracle_large(sparsity):
     assert np.array_equal(_bits(y), _bits(ref))
 
 
+@pytest.mark.parametrize("rows", [1, 3, 5, 31, 33, 1027])
+def test_prune_row_counts_and_threshold_jumps(rows):
+    """A warp prunes 4 consecutive rows and starts each select from the previous row's threshold: row counts that leave partial
+    warps / partial CTAs, and neighbouring rows whose thresholds are far apart (the hint misses: full search), tiny or huge."""
+    from mustafar_b200 import pruning
+    x = _randn((1, 1, rows, 128), rows)
+    scale = torch.tensor([1.0, 1e-4, 3e4, 1.0, 6e-8, 1.0, 255.0, 0.0])[torch.arange(rows) % 8]
+    x = (x.float() * scale[None, None, :, None]).half()  # includes subnormals, values near the fp16 maximum and all-zero rows
+    for s in (0.5, 0.7, 0.01):
+        y = pruning.dh_prune_key(x.cuda(), s).cpu().numpy()
+        assert np.array_equal(_bits(y), _bits(O.prune_rows(x.numpy(), s))), (rows, s)
+
+
 def test_prune_matches_torch_kthvalue_formulation():
     """The reference's literal torch expression (llama_mustafar_kernel.py:97-110), evaluated on the GPU."""
     from mustafar_b200 import pruning
@@ -423,6 +436,33 @@ def test_prefill_single_pass_bit_exact(b, hkv, T, ks, vs, layout):
     assert cache.comp_len == L and cache.win_len == T - L
     _check_prompt_streams(cache, kp, vp, L, ks, vs)
     cache.check_overflow()
+
+
+def test_compression_with_thresholds_that_jump_between_rows():
+    """The select inside the compression kernels starts from the previous row's threshold (a 1024-ulp window) and falls back to
+    the full search when the answer is elsewhere: rows whose magnitudes differ by orders of magnitude, subnormal rows, rows near
+    the fp16 maximum and all-zero rows, through the prefill launch, the decode-time chunk append and the two-pass list API."""
+    from mustafar_b200 import compression
+    from mustafar_b200.attention import MustafarKVCache
+    b, hkv, T, s = 2, 2, 256 * 2 + 40, 0.5
+    scale = torch.tensor([1.0, 1e-4, 3e4, 1.0, 6e-8, 1.0, 255.0, 0.0, 1.0, 1.0, 0.01])[torch.arange(T + 256) % 11]
+    mk = lambda seed: (_randn((b, hkv, T + 256, 128), seed).float() * scale[None, None, :, None]).half()
+    k, v = mk(61), mk(62)
+    cache = MustafarKVCache(b, hkv, 1, T + 600, s, s)
+    cache.prefill(k[:, :, :T].cuda(), v[:, :, :T].cuda())
+    L = O.compressed_length(T)
+    _check_prompt_streams(cache, k[:, :, :T].numpy(), v[:, :, :T].numpy(), L, s, s)
+    for t in range(T, T + 256):  # the window reaches 288 rows: one chunk append
+        cache.append(k[:, :, t:t + 1].cuda(), v[:, :, t:t + 1].cuda())
+        cache.maybe_compress()
+    assert cache.comp_len == L + 256
+    _check_prompt_streams(cache, k.numpy(), v.numpy(), L + 256, s, s)
+    cache.check_overflow()
+    flat = k[:, :, :512].reshape(b * hkv, 512, 128)
+    bmp, acc, packed = compression.prune_convert_key_batched(flat.cuda(), s)
+    rb, ra, rp = O.convert_key_batched(O.prune_rows(flat.numpy(), s))
+    assert np.array_equal(bmp.cpu().numpy(), rb) and np.array_equal(acc.cpu().numpy(), ra)
+    assert all(np.array_equal(_bits(a.cpu().numpy()), _bits(r)) for a, r in zip(packed, rp))
 
 
 def test_prefill_long_chain_and_append_offset():
