@@ -127,9 +127,12 @@ __device__ __forceinline__ uint2 prune4(uint2 v, int k, uint32_t* hint = nullptr
     return make_uint2(v.x & keep_lo, v.y & keep_hi);
 }
 
-// One warp prunes kPruneRowsPerWarp consecutive token rows: all loads are issued first, and each select starts from the
+// One warp prunes kPruneRowsPerWarp consecutive token rows ([256, 32512, 128]: 1 row 1.52 ms, 2 rows 1.42, 4 rows 1.25, 8 rows 1.21): all loads are issued first, and each select starts from the
 // previous row's threshold (warp_kth_smallest_near).
-constexpr int kPruneRowsPerWarp = 4;
+#ifndef MFB_PRUNE_ROWS_PER_WARP
+#define MFB_PRUNE_ROWS_PER_WARP 8
+#endif
+constexpr int kPruneRowsPerWarp = MFB_PRUNE_ROWS_PER_WARP;
 __global__ void __launch_bounds__(256) prune_rows_kernel(const uint2* __restrict__ x, uint2* __restrict__ y,
                                                          int64_t rows, int k) {
     const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * kPruneRowsPerWarp;
