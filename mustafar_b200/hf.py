@@ -278,6 +278,7 @@ class GraphedDecoder:
         self._stale = True  # the captured launches no longer match the cache (or nothing is captured yet)
         self.captures = 0
         self.rope_fused = False
+        self._filled = 0
         self.ids = self.pos = self.slot = self.tokens = self.logits = None
 
     def _buffers(self, batch: int):
@@ -345,6 +346,7 @@ class GraphedDecoder:
         self.ids.copy_(first)
         self.pos.fill_(t)
         self.slot.fill_(1)
+        self._filled = 1  # host mirror of `slot`: tokens recorded so far
         self._stale = True
         return first[:, 0]
 
@@ -355,6 +357,8 @@ class GraphedDecoder:
         layers = self.cache.layers
         if self.ids is None:
             raise ValueError("GraphedDecoder.step: call prefill() first")
+        if self._filled >= self.capacity:
+            raise ValueError(f"GraphedDecoder.step: the token buffer holds max_new_tokens = {self.capacity} tokens")
         for l in layers:
             if l.kv.win_len + 1 > l.kv.win_cap:
                 raise ValueError("GraphedDecoder.step: window capacity exceeded")
@@ -363,6 +367,7 @@ class GraphedDecoder:
         if self._stale:
             self._capture()
         self._graph.replay()
+        self._filled += 1
         compressed = False
         for l in layers:  # host mirrors of what the graph did on the device, then the reference's compression schedule
             l.seen_tokens += 1

@@ -175,3 +175,9 @@ def test_graphed_decoder_generate_matches_hf_generate():
     assert first_diff >= 290 + 8, first_diff
     with pytest.raises(ValueError):
         mhf.GraphedDecoder(model, mhf.MustafarCache(cfg, 0.5, 0.5, max_tokens=400), max_new_tokens=4).generate(ids, 5)
+    small = mhf.GraphedDecoder(model, mhf.MustafarCache(cfg, 0.5, 0.5, max_tokens=400), max_new_tokens=3)
+    with pytest.raises(ValueError):
+        small.step()  # no prompt yet
+    small.generate(ids, 3)
+    with pytest.raises(ValueError):
+        small.step()  # the token buffer is full: refused on the host, not a device-side index error
