@@ -183,7 +183,8 @@ typedef struct mfb200_decode_params {
     int32_t workspace_kb; /* size of `workspace` in KB (rounded down); 0 = not checked.  When set, a launch whose plan needs
                              more is refused with MFB200_EINVAL instead of writing past the buffer. */
     int32_t plan_hint;    /* work decomposition: 0 = chosen from the geometry (production), n > 0 = flat plan with n compressed
-                             CTAs, < 0 = never the flat plan (tests / tuning; size the workspace with the same hint) */
+                             CTAs, < 0 = never the flat plan, -k (k > 1) additionally at least k blocks per compressed CTA
+                             (tests / tuning; size the workspace with the same hint) */
     int32_t reserved0;    /* must be 0 */
     /* query / output: fp16 [B, Hq, 128] contiguous */
     const void* q;

@@ -40,6 +40,11 @@ MHA = [(1, 32, 1, 4096, 0.5), (8, 32, 1, 4096, 0.5), (32, 8, 1, 8192, 0.7), (4, 
 PERF = [(16, 8, 4, 8192, 0.7), (4, 8, 4, 32768, 0.5), (32, 8, 4, 32768, 0.5), (1, 32, 1, 4096, 0.5), (8, 32, 1, 4096, 0.5), (4, 32, 1, 32768, 0.7)]
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "b1":  # batch-1 latency against the work decomposition (plan_hint: n > 0 flat plan with n CTAs, -k uniform >= k blocks/split)
+        for shape in ((1, 8, 4, 4096, 0.5), (1, 8, 4, 2048, 0.7), (1, 8, 4, 16384, 0.5), (4, 8, 4, 4096, 0.5), (1, 8, 1, 4096, 0.5),
+                      (1, 32, 1, 4096, 0.5), (1, 32, 1, 2048, 0.5), (1, 4, 8, 4096, 0.5)):
+            for hint in (0, -2, -3, -4, -6, -8):
+                case(*shape, hint, check=False)
     if which == "perf":
         for args in PERF: case(*args, check=False)
     for args in (GQA if which in ("gqa", "all") else []) + (MHA if which in ("mha", "all") else []):
