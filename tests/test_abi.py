@@ -56,6 +56,25 @@ def test_argument_validation_without_gpu(lib):
     assert lib.mfb200_sparse_decode_attention(C.byref(p), None) == -1
 
 
+def test_plan_never_cuts_finer_than_four_blocks_per_cta(lib):
+    """Few-unit launches: the uniform plan keeps >= 4 blocks (256 tokens) per compressed CTA instead of spending every resident
+    slot (8 units x 60 blocks on 296 slots used to become 37 splits per unit); plan_hint = -k moves the minimum (tuning)."""
+    ws, cb = C.c_size_t(0), C.c_size_t(0)
+    plan = lambda *a: lib.mfb200_decode_plan(*a, C.byref(ws), C.byref(cb))
+    wsplits = 4  # a 256-row window = 4 chunks of 64
+    assert plan(1, 8, 4, 3840, 256, 148, 0) == 15 + wsplits      # 60 blocks per unit -> 15 splits of 4
+    assert plan(1, 4, 8, 3840, 256, 148, 0) == 15 + wsplits
+    assert plan(1, 8, 4, 1792, 256, 148, 0) == 7 + wsplits       # 28 blocks -> 7 splits of 4
+    assert plan(1, 8, 4, 128, 40, 148, 0) == 1 + 1               # 2 blocks: one CTA
+    assert plan(1, 32, 1, 3840, 256, 148, 0) == 14 + wsplits     # config 1 already has 4.3 blocks per CTA: unchanged
+    assert plan(1, 32, 1, 3840, 256, 148, -8) == 8 + wsplits     # tuning override: >= 8 blocks per split
+    assert plan(1, 32, 1, 3840, 256, 148, -1) == 14 + wsplits    # -1 = never flat, default minimum
+    for g, hkv in ((4, 8), (8, 4), (1, 8), (2, 16)):
+        for comp in (64, 192, 256, 1024, 3840):
+            for hint in (0, -2, -6):
+                assert lib.mfb200_decode_plan_check(1, hkv, g, comp, 64, 148, hint) >= 0, (g, hkv, comp, hint)
+
+
 def test_no_cpu_fallback():
     import torch
     from mustafar_b200 import compression, pruning
