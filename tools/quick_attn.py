@@ -45,6 +45,11 @@ if __name__ == "__main__":
                       (1, 32, 1, 4096, 0.5), (1, 32, 1, 2048, 0.5), (1, 4, 8, 4096, 0.5)):
             for hint in (0, -2, -3, -4, -6, -8):
                 case(*shape, hint, check=False)
+    if which == "mid":  # mid-size launches: automatic plan vs a forced flat cut over the resident slots vs coarser uniform splits
+        for shape, slots in (((2, 8, 4, 4096, 0.5), 296), ((4, 8, 4, 8192, 0.7), 296), ((8, 8, 4, 4096, 0.5), 296),
+                             ((2, 32, 1, 4096, 0.5), 444), ((4, 32, 1, 4096, 0.5), 444), ((16, 32, 1, 4096, 0.5), 444)):
+            for hint in (0, slots, slots // 2, -6, -8):
+                case(*shape, hint, check=False)
     if which == "perf":
         for args in PERF: case(*args, check=False)
     for args in (GQA if which in ("gqa", "all") else []) + (MHA if which in ("mha", "all") else []):
