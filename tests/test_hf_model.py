@@ -181,3 +181,45 @@ def test_graphed_decoder_generate_matches_hf_generate():
     small.generate(ids, 3)
     with pytest.raises(ValueError):
         small.step()  # the token buffer is full: refused on the host, not a device-side index error
+
+
+def test_deferred_rope_patch_is_scoped_to_the_capture_and_the_thread():
+    """`_DeferredRope` (CPU logic only): inside the context the model file's apply_rotary_pos_emb hands 1-token fp16 q / k through
+    and leaves (cos, sin) with the step; anything else - several tokens, another dtype, another thread - gets the stock function;
+    the module global is restored on exit."""
+    import threading
+    import types
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from transformers.models.llama import modeling_llama
+    import mustafar_b200.hf as mhf
+    cfg = LlamaConfig(vocab_size=64, hidden_size=128, intermediate_size=64, num_hidden_layers=1, num_attention_heads=1,
+                      num_key_value_heads=1, head_dim=128)
+    model = LlamaForCausalLM(cfg)
+    stock = modeling_llama.apply_rotary_pos_emb
+    step = types.SimpleNamespace(rope=None)
+    q, k = torch.randn(2, 1, 1, 128).half(), torch.randn(2, 1, 1, 128).half()
+    ang = torch.rand(2, 1, 64)
+    cos, sin = torch.cat([ang, ang], -1).cos().half(), torch.cat([ang, ang], -1).sin().half()
+    want_q, want_k = stock(q.float(), k.float(), cos.float(), sin.float())
+    with mhf._DeferredRope(model, step, enabled=True):
+        assert modeling_llama.apply_rotary_pos_emb is not stock
+        got_q, got_k = modeling_llama.apply_rotary_pos_emb(q, k, cos, sin)
+        assert got_q is q and got_k is k and step.rope[0] is cos and step.rope[1] is sin
+        # two tokens: not a decode step -> stock path, and the stale (cos, sin) are dropped
+        q2, k2 = torch.randn(2, 1, 2, 128).half(), torch.randn(2, 1, 2, 128).half()
+        cos2, sin2 = cos.expand(2, 2, 128).contiguous(), sin.expand(2, 2, 128).contiguous()
+        r_q, _ = modeling_llama.apply_rotary_pos_emb(q2, k2, cos2, sin2)
+        assert r_q is not q2 and step.rope is None
+        # fp32 tensors: stock path
+        f_q, _ = modeling_llama.apply_rotary_pos_emb(q.float(), k.float(), cos.float(), sin.float())
+        assert torch.equal(f_q, want_q) and step.rope is None
+        # another thread keeps the stock behaviour
+        box = {}
+        t = threading.Thread(target=lambda: box.update(r=modeling_llama.apply_rotary_pos_emb(q.float(), k.float(), cos.float(), sin.float())))
+        t.start(); t.join()
+        assert torch.equal(box["r"][0], want_q) and torch.equal(box["r"][1], want_k)
+    assert modeling_llama.apply_rotary_pos_emb is stock
+    with mhf._DeferredRope(model, step, enabled=False):  # fuse_rope=False, or no static step: nothing is patched
+        assert modeling_llama.apply_rotary_pos_emb is stock
+    with mhf._DeferredRope(model, None, enabled=True):
+        assert modeling_llama.apply_rotary_pos_emb is stock
