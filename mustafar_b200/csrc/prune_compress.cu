@@ -157,23 +157,37 @@ __global__ void __launch_bounds__(256) prune_rows_kernel(const uint2* __restrict
 // arbitrary subset of the tied elements (torch.sort is not stable), here every tied element survives.
 __global__ void __launch_bounds__(256) prune_rows_scored_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w,
                                                                 uint2* __restrict__ y, int64_t rows, int64_t rows_per_unit, int k) {
-    const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    // like prune_rows_kernel: a warp takes kPruneRowsPerWarp consecutive rows, loads first, hinted selects after
+    const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * kPruneRowsPerWarp;
+    if (row0 >= rows) return;
     const uint32_t lane = lane_id();
-    const uint2 v = x[row * 32 + lane];
-    uint32_t kx, ky;
-    if (rows_per_unit > 0) {  // score = |x * w[unit]|
-        const uint2 ww = w[(row / rows_per_unit) * 32 + lane];
-        const __half2 s0 = __hmul2_rn(*reinterpret_cast<const __half2*>(&v.x), *reinterpret_cast<const __half2*>(&ww.x));
-        const __half2 s1 = __hmul2_rn(*reinterpret_cast<const __half2*>(&v.y), *reinterpret_cast<const __half2*>(&ww.y));
-        kx = *reinterpret_cast<const uint32_t*>(&s0) & 0x7fff7fffu, ky = *reinterpret_cast<const uint32_t*>(&s1) & 0x7fff7fffu;
-    } else {  // the caller's own score rows (the decode-time form: an accumulated score, `:131-145`)
-        const uint2 sc = w[row * 32 + lane];
-        kx = sc.x & 0x7fff7fffu, ky = sc.y & 0x7fff7fffu;
-    }
-    const uint32_t tb = warp_kth_smallest(kx, ky, k) * 0x10001u;
-    const uint32_t gx = ((kx | 0x80008000u) - tb) & 0x80008000u, gy = ((ky | 0x80008000u) - tb) & 0x80008000u;
-    y[row * 32 + lane] = make_uint2(v.x & ((gx - (gx >> 15)) | 0x80008000u), v.y & ((gy - (gy >> 15)) | 0x80008000u));
+    const int n = static_cast<int>(min(static_cast<int64_t>(kPruneRowsPerWarp), rows - row0));
+    uint2 v[kPruneRowsPerWarp], sc[kPruneRowsPerWarp];
+#pragma unroll
+    for (int i = 0; i < kPruneRowsPerWarp; ++i)
+        if (i < n) {
+            v[i] = x[(row0 + i) * 32 + lane];
+            // rows_per_unit > 0: w = the unit's weights, score = |x * w|; else w holds the caller's own score rows (the
+            // decode-time form: an accumulated score, `:131-145`)
+            sc[i] = w[(rows_per_unit > 0 ? (row0 + i) / rows_per_unit : row0 + i) * 32 + lane];
+        }
+    uint32_t hint = kNoHint;
+#pragma unroll
+    for (int i = 0; i < kPruneRowsPerWarp; ++i)
+        if (i < n) {
+            uint32_t kx, ky;
+            if (rows_per_unit > 0) {
+                const __half2 s0 = __hmul2_rn(*reinterpret_cast<const __half2*>(&v[i].x), *reinterpret_cast<const __half2*>(&sc[i].x));
+                const __half2 s1 = __hmul2_rn(*reinterpret_cast<const __half2*>(&v[i].y), *reinterpret_cast<const __half2*>(&sc[i].y));
+                kx = *reinterpret_cast<const uint32_t*>(&s0) & 0x7fff7fffu, ky = *reinterpret_cast<const uint32_t*>(&s1) & 0x7fff7fffu;
+            } else {
+                kx = sc[i].x & 0x7fff7fffu, ky = sc[i].y & 0x7fff7fffu;
+            }
+            hint = warp_kth_smallest_near(kx, ky, k, hint);
+            const uint32_t tb = hint * 0x10001u;
+            const uint32_t gx = ((kx | 0x80008000u) - tb) & 0x80008000u, gy = ((ky | 0x80008000u) - tb) & 0x80008000u;
+            y[(row0 + i) * 32 + lane] = make_uint2(v[i].x & ((gx - (gx >> 15)) | 0x80008000u), v[i].y & ((gy - (gy >> 15)) | 0x80008000u));
+        }
 }
 
 // Channel-wise value pruning (models/llama_mustafar_Kt_Mag_Vc_Mag.py:107-170): inside every group of `group` consecutive
@@ -705,7 +719,8 @@ extern "C" int mfb200_prune_rows_scored(const void* x, const void* w, void* y, i
     MFB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 7) == 0,
                 "prune_rows_scored: pointers must be 8-byte aligned");
     if (rows == 0) return MFB200_OK;
-    prune_rows_scored_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    prune_rows_scored_kernel<<<static_cast<unsigned>((rows + 8 * kPruneRowsPerWarp - 1) / (8 * kPruneRowsPerWarp)), 256, 0,
+                               static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint2*>(x), static_cast<const uint2*>(w), static_cast<uint2*>(y), rows, rows_per_unit, k);
     return launch_status("prune_rows_scored_kernel");
 }
